@@ -1,0 +1,154 @@
+/* voxbox_b200.h — C ABI of the B200-native vox_box hot path.
+ *
+ * Drop-in boundary for the framewise speech-analysis path of
+ * andrewcsmith/vox_box.rs (Rust extension traits on slices; no FFI of its own).
+ * Every entry point below names the reference interface it replaces
+ * (file:line relative to the reference crate root).  One reference call
+ * processes ONE frame slice; the entry points here are batched over frames
+ * (a reference call == a batch of 1).  INTEGRATION.md shows the Rust
+ * `extern "C"` block and trait impls a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `vbx_ctx` is opaque.
+ *  - unless an entry point ends in `_host`, every data pointer is a DEVICE
+ *    pointer (HBM resident, caller owned, never freed by the library) and the
+ *    call is asynchronous on the context's stream: call vbx_sync() (or any
+ *    `_host` entry point, which synchronises) before reading results.
+ *  - `_host` twins take HOST pointers, stage through the context's scratch
+ *    arena and return when the results are in the caller's buffers.
+ *  - return value: vbx_status.  Calls that can fail per frame (Burg, root
+ *    finding, pitch) also fill an optional `uint8_t status[F]` with the same
+ *    codes; the call returns VBX_OK if it ran, and the Rust shim maps "any frame
+ *    failed" to the matching `Err(VoxBoxError::..)`.
+ *  - there is no CPU fallback: without a usable CUDA device vbx_ctx_create
+ *    fails with VBX_ERR_CUDA.
+ */
+#ifndef VOXBOX_B200_H
+#define VOXBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VBX_API __attribute__((visibility("default")))
+#else
+#define VBX_API
+#endif
+
+/* ---- status codes: error.rs:6-16 `VoxBoxError` ------------------------------ */
+typedef enum vbx_status {
+    VBX_OK = 0,
+    VBX_ERR_LPC = 1,        /* VoxBoxError::LPC("Denum was <= 0.0")                 spectrum.rs:123-125 */
+    VBX_ERR_PITCH = 2,      /* VoxBoxError::Pitch (where the reference panics on NaN, periodic.rs:453) */
+    VBX_ERR_POLYNOMIAL = 3, /* VoxBoxError::Polynomial(..)                     polynomial.rs:95,123,192 */
+    VBX_ERR_WORKSPACE = 4,  /* VoxBoxError::Workspace                                      lib.rs:46-48 */
+    VBX_ERR_CUDA = 5,       /* CUDA runtime failure / no device (no reference analogue)                */
+    VBX_ERR_BADARG = 6,     /* sizes for which the reference would panic (assert!/index)              */
+    VBX_ERR_NOMEM = 7       /* device or pinned allocation failed                                      */
+} vbx_status;
+
+typedef enum vbx_dtype { VBX_F32 = 0, VBX_F64 = 1, VBX_I16 = 2 } vbx_dtype;
+
+/* Window applied while a frame is loaded (the reference's callers window the
+ * frame before calling the trait method):
+ *  HANN_SYMMETRIC = sample::window::Windower::hanning (examples/pitch_detection.rs:23,
+ *                   periodic.rs:493): 0.5(1-cos 2πφ), φ accumulated in steps of 1/(N-1);
+ *  HANN_PERIODIC  = the in-line window of find_formants (lib.rs:66-70): φ = i/N;
+ *  NONE           = frame is used as is (Windower::rectangle, tests/lib.rs:71). */
+typedef enum vbx_window { VBX_WINDOW_NONE = 0, VBX_WINDOW_HANN_SYMMETRIC = 1, VBX_WINDOW_HANN_PERIODIC = 2 } vbx_window;
+
+/* A batch of frames as a strided view: frame f = base[f*frame_stride .. f*frame_stride + frame_len).
+ * frame_stride == frame_len is a packed [F, N] tensor; frame_stride == hop < frame_len is the
+ * overlapped view over contiguous audio that `Windower::{hanning,rectangle}(.., bin, hop)` iterates.
+ * A batch of equally long utterances is a two-level view: with frames_per_segment = J > 0, frame
+ * f = u*J + j starts at base[u*segment_stride + j*frame_stride] (n_frames must be a multiple of J);
+ * frames_per_segment == 0 means one segment holds all frames.
+ * dtype: VBX_F32 samples, or VBX_I16 PCM scaled by 1/32767 on load (tests/lib.rs:17-19). */
+typedef struct vbx_frames {
+    const void* base;
+    int64_t n_frames;
+    int64_t frame_stride;       /* in samples */
+    int64_t frames_per_segment; /* J, or 0 */
+    int64_t segment_stride;     /* in samples; ignored when frames_per_segment == 0 */
+    int32_t frame_len;          /* N */
+    int32_t dtype;        /* vbx_dtype: VBX_F32 or VBX_I16 */
+    int32_t window;       /* vbx_window */
+    int32_t reserved;     /* must be 0 */
+} vbx_frames;
+
+/* #[repr(C)] Resonance<T> { frequency, bandwidth }  spectrum.rs:149-154 */
+typedef struct vbx_resonance_f32 { float frequency, bandwidth; } vbx_resonance_f32;
+typedef struct vbx_resonance_f64 { double frequency, bandwidth; } vbx_resonance_f64;
+/* Pitch<T> { frequency, strength }  periodic.rs:306-310 */
+typedef struct vbx_pitch_f32 { float frequency, strength; } vbx_pitch_f32;
+typedef struct vbx_pitch_f64 { double frequency, strength; } vbx_pitch_f64;
+
+/* lib.rs:26-28 */
+#define VBX_MAX_RESONANCES 32
+#define VBX_MAX_FORMANT_SLOTS 6 /* spectrum.rs:228 FormantSlots */
+VBX_API extern const double VBX_MALE_FORMANT_ESTIMATES[4];
+VBX_API extern const double VBX_FEMALE_FORMANT_ESTIMATES[4];
+
+typedef struct vbx_ctx vbx_ctx;
+
+/* ---- context, memory, errors ------------------------------------------------------ */
+/* One context = one device + one stream + one scratch arena; not thread-safe (use one per host
+ * thread / GPU).  The reference is pure functions on caller buffers (no context). */
+VBX_API int vbx_ctx_create(int device, vbx_ctx** out);
+VBX_API int vbx_ctx_destroy(vbx_ctx* ctx);
+VBX_API int vbx_sync(vbx_ctx* ctx);
+VBX_API void* vbx_ctx_stream(vbx_ctx* ctx);           /* the cudaStream_t the context launches on */
+VBX_API const char* vbx_last_error(vbx_ctx* ctx);     /* message of the last failing call */
+VBX_API const char* vbx_status_str(int status);       /* error.rs:25-32 description() strings */
+VBX_API int vbx_version(void);
+VBX_API int vbx_device_sm_count(vbx_ctx* ctx);
+VBX_API int64_t vbx_kernel_launches(vbx_ctx* ctx);    /* kernels launched by this context so far */
+
+VBX_API int vbx_malloc(vbx_ctx* ctx, size_t bytes, void** dev_out);
+VBX_API int vbx_free(vbx_ctx* ctx, void* dev);
+VBX_API int vbx_malloc_host(vbx_ctx* ctx, size_t bytes, void** host_out); /* pinned */
+VBX_API int vbx_free_host(vbx_ctx* ctx, void* host);
+VBX_API int vbx_memcpy_h2d(vbx_ctx* ctx, void* dev, const void* host, size_t bytes); /* async on ctx stream */
+VBX_API int vbx_memcpy_d2h(vbx_ctx* ctx, void* host, const void* dev, size_t bytes); /* async on ctx stream */
+VBX_API int vbx_memset(vbx_ctx* ctx, void* dev, int value, size_t bytes);
+
+/* Device timing on the context's stream (CUDA events), for callers without a CUDA binding. */
+VBX_API int vbx_timer_start(vbx_ctx* ctx);
+VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms_out); /* synchronises */
+
+/* Measured pipe peaks of this device (dependent-free FMA loops on every SM), used as roofline
+ * denominators for the FP32/FP64-bound kernels.  Values in TFLOP/s (2 flop per FMA). */
+VBX_API int vbx_measure_peaks(vbx_ctx* ctx, double* fp32_tflops, double* fp64_tflops);
+
+/* Window table exactly as the reference's callers compute it, in f64 on the host
+ * (sample::window::Window phase accumulation; lib.rs:66-70).  out: n doubles (host). */
+VBX_API int vbx_window_table_host(int window, int32_t n, double* out);
+
+/* ---- periodic.rs:265-289  Autocorrelate::{autocorrelate_mut, autocorrelate} ------------ */
+/* r_out[f][lag] = x[0] + Σ_{i=1}^{N-lag-1} x[i]·x[i+lag] on the (windowed) frame, lag < n_lags <= N,
+ * accumulated in fp64.  r_out: [F][n_lags] of out_dtype (VBX_F32|VBX_F64). */
+VBX_API int vbx_autocorrelate(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lags, void* r_out, int32_t out_dtype);
+VBX_API int vbx_autocorrelate_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lags, void* r_out,
+                                   int32_t out_dtype);
+
+/* ---- spectrum.rs:50-92  LPC::{lpc_mut, lpc} (Levinson–Durbin) + LPCSolver ---------------- */
+/* r: [F][r_stride] of r_dtype with r_stride >= p+1.  ac_out: [F][p+1] (ac[0] = 1, error-filter
+ * sign), kc_out: [F][p] reflection coefficients (may be NULL).  fp64 arithmetic. */
+VBX_API int vbx_lpc_levinson(vbx_ctx* ctx, const void* r, int32_t r_dtype, int64_t n_frames, int32_t r_stride,
+                             int32_t p, void* ac_out, void* kc_out, int32_t out_dtype);
+
+/* Fused north-star chain (config C2): window → autocorrelate(p+1) → lpc(p) in one kernel.
+ * Any of r_out [F][p+1], ac_out [F][p+1], kc_out [F][p] may be NULL. */
+VBX_API int vbx_lpc(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out,
+                    int32_t out_dtype);
+VBX_API int vbx_lpc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out,
+                         int32_t out_dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXBOX_B200_H */

@@ -1,0 +1,90 @@
+// vbx_internal.cuh — shared internals of libvoxbox_b200 (context, error plumbing, device helpers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/voxbox_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct vbx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;  // max dynamic shared memory per block (opt-in)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // scratch arena (device) and pinned staging (host) — grow-only, reused across calls
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // window tables (device, f64), keyed by (kind << 32 | n)
+    std::map<uint64_t, double*> windows;
+};
+
+int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);
+int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
+int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
+int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out);  // cached device table (ones for NONE)
+void vbx_window_fill_host(int kind, int n, double* out);
+
+#define VBX_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return vbx_fail((ctx), VBX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define VBX_CHECK_LAUNCH(ctx, name)                                                                  \
+    do {                                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                                        \
+        if (e__ != cudaSuccess)                                                                      \
+            return vbx_fail((ctx), VBX_ERR_CUDA, "launch of %s failed: %s", (name), cudaGetErrorString(e__)); \
+        (ctx)->launches++;                                                                           \
+    } while (0)
+
+#define VBX_REQUIRE(ctx, cond, ...)                                                                  \
+    do {                                                                                             \
+        if (!(cond)) return vbx_fail((ctx), VBX_ERR_BADARG, __VA_ARGS__);                            \
+    } while (0)
+
+static inline size_t vbx_dtype_size(int dt) { return dt == VBX_F64 ? 8 : (dt == VBX_I16 ? 2 : 4); }
+
+// validates a vbx_frames descriptor (device or host pointers alike)
+int vbx_check_frames(vbx_ctx* ctx, const vbx_frames* fr);
+// number of samples spanned by the strided view (0 if n_frames == 0)
+static inline int64_t vbx_frames_per_segment(const vbx_frames* fr) {
+    return fr->frames_per_segment > 0 ? fr->frames_per_segment : fr->n_frames;
+}
+static inline int64_t vbx_frames_extent(const vbx_frames* fr) {
+    if (fr->n_frames <= 0) return 0;
+    const int64_t J = vbx_frames_per_segment(fr), segs = fr->n_frames / J;
+    return (segs - 1) * (fr->frames_per_segment > 0 ? fr->segment_stride : 0) + (J - 1) * fr->frame_stride + fr->frame_len;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename T> __device__ __forceinline__ T vbx_ldg(const T* p) { return __ldg(p); }
+
+// sample load with dtype dispatch (F32, or I16 PCM scaled by 1/32767 — tests/lib.rs:17-19)
+template <typename TIn> __device__ __forceinline__ float vbx_load_sample(const TIn* p);
+template <> __device__ __forceinline__ float vbx_load_sample<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float vbx_load_sample<int16_t>(const int16_t* p) { return (float)__ldg(p); }
+
+template <typename TOut> __device__ __forceinline__ void vbx_store(TOut* p, double v) { *p = (TOut)v; }
+
+__device__ __forceinline__ double vbx_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+#endif

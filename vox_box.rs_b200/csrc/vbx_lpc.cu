@@ -1,0 +1,517 @@
+// vbx_lpc.cu — windowed autocorrelation (fp64 accumulate) + Levinson–Durbin, fused.
+//
+// Replaces, batched over frames:
+//   periodic.rs:265-289  Autocorrelate::autocorrelate_mut   r[lag] = x[0] + Σ_{i>=1} x[i]·x[i+lag]
+//   spectrum.rs:63-84    LPC::lpc_mut (Levinson–Durbin)
+// with the window multiply of the reference's callers (Windower::hanning / lib.rs:66-70) fused
+// into the load.
+//
+// Kernel shape: a CTA stages the contiguous audio span of G overlapping frames
+// in shared memory once (padded so that frame starts fall in distinct banks), then every group of K
+// lanes owns one frame.  A lane walks its part of the frame sequentially with the last L windowed
+// samples in a register ring and L fp64 accumulators (L = p+1 lags, all static indices): per sample
+// 1 LDS (sample) + 1 LDS.64 (window) + 1 DMUL + L DFMA, no cross-lane traffic in the loop.  K>1
+// partial sums are combined with shuffles; Levinson then runs one thread per frame out of shared
+// memory and the results leave through a coalesced store.
+#include "vbx_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct LpcParams {
+    const void* base;      // samples
+    const double* win;     // [n] device window table (ones for WINDOW_NONE)
+    void* r_out;           // [F][L]   or null
+    void* ac_out;          // [F][L]   or null
+    void* kc_out;          // [F][L-1] or null
+    int64_t n_frames;
+    int64_t stride;        // frame stride in samples
+    int64_t seg_frames;    // frames per segment (utterance); CTAs never straddle segments
+    int64_t seg_stride;    // samples between segment starts
+    int ctas_per_seg;
+    int n;                 // frame length
+    int k;                 // lanes per frame (power of two <= 32)
+    int frames_per_cta;    // G = kThreads / k
+    int sv;                // virtual stride inside shared memory: min(stride, n)
+    int pad;               // 0/1: one pad word after every sv samples so that (sv+pad) is odd
+    int part;              // samples per lane part: ceil(n / k)
+    int span_words;        // shared-memory words reserved for the padded span
+    int out_f64;           // outputs are double (else float)
+    int do_levinson;
+};
+
+// Levinson–Durbin exactly as spectrum.rs:63-84 (no zero guard: err == 0 propagates inf/NaN).
+template <int P>
+__device__ __forceinline__ void levinson(const double* __restrict__ r, double* __restrict__ ac, double* __restrict__ kc) {
+    double a[P + 1];
+    double err = r[0];
+    a[0] = 1.0;
+#pragma unroll
+    for (int i = 1; i <= P; ++i) a[i] = 0.0;
+#pragma unroll
+    for (int i = 1; i <= P; ++i) {
+        double acc = r[i];
+#pragma unroll
+        for (int j = 1; j < i; ++j) acc = acc + a[j] * r[i - j];
+        const double k = (-acc) / err;
+        kc[i - 1] = k;
+        a[i] = k;
+        // ac[j] += k·tmp[i-j] for j in 1..i-1 with tmp = the pre-update copy (spectrum.rs:76-81):
+        // updated pairwise so both ends read old values and no copy is needed
+#pragma unroll
+        for (int j = 1; 2 * j < i; ++j) {
+            const double lo = a[j], hi = a[i - j];
+            a[j] = lo + k * hi;
+            a[i - j] = hi + k * lo;
+        }
+        if ((i & 1) == 0) a[i / 2] = a[i / 2] + k * a[i / 2];
+        err = err * (1.0 - k * k);
+    }
+#pragma unroll
+    for (int i = 0; i <= P; ++i) ac[i] = a[i];
+}
+
+template <int L, typename TIn>
+__global__ void __launch_bounds__(kThreads) lpc_fused_kernel(const LpcParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_win = reinterpret_cast<double*>(smem_raw);                 // [n]
+    float* s_span = reinterpret_cast<float*>(s_win + P.n);               // padded span
+    double* s_out = reinterpret_cast<double*>(s_win + P.n);              // staging, reuses the span after a barrier
+
+    const int tid = threadIdx.x;
+    const int G = P.frames_per_cta;
+    const int64_t seg = blockIdx.x / P.ctas_per_seg;
+    const int64_t j0 = (int64_t)(blockIdx.x - seg * P.ctas_per_seg) * G;  // first frame of this CTA inside its segment
+    const int64_t g0 = seg * P.seg_frames + j0;                           // ... and in the batch (output row)
+    const int Gc = (int)min((int64_t)G, P.seg_frames - j0);
+    const int n = P.n, sv = P.sv, pad = P.pad;
+    const TIn* __restrict__ base = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride;
+
+    // ---- stage window + span -------------------------------------------------------------
+    for (int i = tid; i < n; i += kThreads) s_win[i] = __ldg(P.win + i);
+    if (P.stride <= (int64_t)n) {
+        // overlapped / packed frames: one contiguous run of (Gc-1)·stride + n samples
+        const TIn* src = base + j0 * P.stride;
+        const int total = (Gc - 1) * sv + n;
+        const int nblk = (total + sv - 1) / sv;
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int b = warp; b < nblk; b += kThreads / 32) {
+            const int lo = b * sv, cnt = min(sv, total - lo);
+            for (int j = lane; j < cnt; j += 32) s_span[lo + j + pad * b] = vbx_load_sample<TIn>(src + lo + j);
+        }
+    } else {
+        // gapped frames: each frame's n samples land in consecutive blocks of sv == n words
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int g = warp; g < Gc; g += kThreads / 32) {
+            const TIn* src = base + (j0 + g) * P.stride;
+            for (int j = lane; j < n; j += 32) s_span[g * (sv + pad) + j] = vbx_load_sample<TIn>(src + j);
+        }
+    }
+    __syncthreads();
+
+    // ---- per-lane partial autocorrelation -------------------------------------------------
+    const int k = P.k;
+    const int g = tid / k, q = tid - g * k;
+    double acc[L], h[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) { acc[j] = 0.0; h[j] = 0.0; }
+    double x0 = 0.0;  // frame sample 0 (windowed) for the reference's "+ x[0]" seed
+    if (g < Gc) {
+        const int i_begin = q * P.part;
+        const int i_end = min(n, i_begin + P.part);
+        // running position in the padded span: pos(i) = g·(sv+pad) + i + pad·(i / sv)
+        int i = (q == 0) ? 0 : max(0, i_begin - (L - 1));
+        int blk = i / sv;
+        int pos = g * (sv + pad) + i + pad * blk;
+        int left = sv - (i - blk * sv);  // samples until the next pad word
+        auto fetch = [&](int idx) -> double {
+            double v = (double)s_span[pos] * s_win[idx];
+            ++pos;
+            if (--left == 0) { pos += pad; left = sv; }
+            return v;
+        };
+        if (q != 0) {
+            // history: h[j] = xw[i_begin - L + j], j = 1..L-1 (i_begin >= L-1 is guaranteed by the host)
+#pragma unroll
+            for (int j = 1; j < L; ++j) { h[j] = fetch(i); ++i; }
+        }
+        // full chunks of L samples: ring slot u holds xw[i+u]; lag products use static slots
+        for (; i + L <= i_end; i += L) {
+#pragma unroll
+            for (int u = 0; u < L; ++u) {
+                const double xn = fetch(i + u);
+                h[u] = xn;
+#pragma unroll
+                for (int lag = 0; lag < L; ++lag) acc[lag] = fma(xn, h[(u - lag + L) % L], acc[lag]);
+            }
+            if (q == 0 && i == 0) {
+                // reference quirk (periodic.rs:284): the fold is seeded with x[0] and skips the i = 0
+                // product, so r[lag] = true_r[lag] − x0·x[lag] + x0.  After the first chunk h[j] = xw[j].
+                x0 = h[0];
+#pragma unroll
+                for (int lag = 0; lag < L; ++lag) acc[lag] = fma(x0, 1.0 - h[lag], acc[lag]);
+            }
+        }
+        // tail chunk (< L samples): zero-fed slots contribute nothing
+        if (i < i_end) {
+            const bool first = (q == 0 && i == 0);
+#pragma unroll
+            for (int u = 0; u < L; ++u) {
+                const double xn = (i + u < i_end) ? fetch(i + u) : 0.0;
+                h[u] = xn;
+#pragma unroll
+                for (int lag = 0; lag < L; ++lag) acc[lag] = fma(xn, h[(u - lag + L) % L], acc[lag]);
+            }
+            if (first) {  // n < L: lags >= n see x[lag] = 0, r[lag] = x0 as in the reference
+                x0 = h[0];
+#pragma unroll
+                for (int lag = 0; lag < L; ++lag) acc[lag] = fma(x0, 1.0 - h[lag], acc[lag]);
+            }
+        }
+    }
+    // combine the K parts of a frame (K consecutive lanes, K | 32)
+    for (int m = 1; m < k; m <<= 1) {
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) acc[lag] += vbx_shfl_xor(acc[lag], m);
+    }
+    __syncthreads();  // everyone is done reading the span; reuse it as output staging
+
+    double* s_r = s_out;                  // [G][L]
+    double* s_ac = s_r + G * L;           // [G][L]
+    double* s_kc = s_ac + G * L;          // [G][L-1]
+    if (g < Gc && q == 0) {
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) s_r[g * L + lag] = acc[lag];
+    }
+    __syncthreads();
+    if (P.do_levinson && tid < Gc) {
+        double r[L], ac[L], kc[L - 1];
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) r[lag] = s_r[tid * L + lag];
+        levinson<L - 1>(r, ac, kc);
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) s_ac[tid * L + lag] = ac[lag];
+#pragma unroll
+        for (int j = 0; j < L - 1; ++j) s_kc[tid * (L - 1) + j] = kc[j];
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out --------------------------------------------------------------
+    auto store = [&](void* out, const double* src, int per_frame) {
+        if (!out) return;
+        const int total = Gc * per_frame;
+        const int64_t off = g0 * per_frame;
+        if (P.out_f64) {
+            double* o = reinterpret_cast<double*>(out) + off;
+            for (int idx = tid; idx < total; idx += kThreads) o[idx] = src[idx];
+        } else {
+            float* o = reinterpret_cast<float*>(out) + off;
+            for (int idx = tid; idx < total; idx += kThreads) o[idx] = (float)src[idx];
+        }
+    };
+    store(P.r_out, s_r, L);
+    if (P.do_levinson) {
+        store(P.ac_out, s_ac, L);
+        store(P.kc_out, s_kc, L - 1);
+    }
+}
+
+// Generic fallback (any n_lags / frame length): one CTA per frame, windowed frame as fp64 in
+// shared memory when it fits, lags strided over warps with a shuffle reduction.
+template <typename TIn>
+__global__ void __launch_bounds__(256) autocorr_generic_kernel(const TIn* __restrict__ base, const double* __restrict__ win,
+                                                               int64_t stride, int64_t seg_frames, int64_t seg_stride, int n,
+                                                               int n_lags, void* r_out, int out_f64, int use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_x = reinterpret_cast<double*>(smem_raw);
+    const int64_t f = blockIdx.x;
+    const int64_t seg = f / seg_frames;
+    const TIn* x = base + seg * seg_stride + (f - seg * seg_frames) * stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (use_smem) {
+        for (int i = tid; i < n; i += blockDim.x) s_x[i] = (double)vbx_load_sample<TIn>(x + i) * __ldg(win + i);
+        __syncthreads();
+    }
+    auto xw = [&](int i) -> double {
+        return use_smem ? s_x[i] : (double)vbx_load_sample<TIn>(x + i) * __ldg(win + i);
+    };
+    const double x0 = xw(0);
+    for (int lag = warp; lag < n_lags; lag += nwarps) {
+        double acc = 0.0;
+        for (int i = 1 + lane; i + lag < n; i += 32) acc = fma(xw(i), xw(i + lag), acc);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += vbx_shfl_xor(acc, m);
+        if (lane == 0) {
+            const double r = x0 + acc;
+            if (out_f64) reinterpret_cast<double*>(r_out)[f * n_lags + lag] = r;
+            else reinterpret_cast<float*>(r_out)[f * n_lags + lag] = (float)r;
+        }
+    }
+}
+
+// Stand-alone Levinson: one thread per frame, r read from global (f32 or f64).
+template <int PORD>
+__global__ void __launch_bounds__(128) levinson_kernel(const void* __restrict__ r_in, int r_f64, int64_t n_frames,
+                                                       int r_stride, void* ac_out, void* kc_out, int out_f64) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    double r[PORD + 1], ac[PORD + 1], kc[PORD];
+#pragma unroll
+    for (int i = 0; i <= PORD; ++i)
+        r[i] = r_f64 ? reinterpret_cast<const double*>(r_in)[f * r_stride + i]
+                     : (double)reinterpret_cast<const float*>(r_in)[f * r_stride + i];
+    levinson<PORD>(r, ac, kc);
+    if (ac_out) {
+#pragma unroll
+        for (int i = 0; i <= PORD; ++i) {
+            if (out_f64) reinterpret_cast<double*>(ac_out)[f * (PORD + 1) + i] = ac[i];
+            else reinterpret_cast<float*>(ac_out)[f * (PORD + 1) + i] = (float)ac[i];
+        }
+    }
+    if (kc_out) {
+#pragma unroll
+        for (int i = 0; i < PORD; ++i) {
+            if (out_f64) reinterpret_cast<double*>(kc_out)[f * PORD + i] = kc[i];
+            else reinterpret_cast<float*>(kc_out)[f * PORD + i] = (float)kc[i];
+        }
+    }
+}
+
+constexpr int kMaxFastLags = 25;  // fused kernel instantiated for 2..25 lags (LPC orders 1..24)
+
+typedef void (*lpc_kernel_t)(const LpcParams);
+template <typename TIn, int L> struct LpcTable {
+    static void fill(lpc_kernel_t* t) {
+        t[L] = lpc_fused_kernel<L, TIn>;
+        LpcTable<TIn, L - 1>::fill(t);
+    }
+};
+template <typename TIn> struct LpcTable<TIn, 1> {
+    static void fill(lpc_kernel_t*) {}
+};
+
+typedef void (*lev_kernel_t)(const void*, int, int64_t, int, void*, void*, int);
+template <int P> struct LevTable {
+    static void fill(lev_kernel_t* t) {
+        t[P] = levinson_kernel<P>;
+        LevTable<P - 1>::fill(t);
+    }
+};
+template <> struct LevTable<0> {
+    static void fill(lev_kernel_t*) {}
+};
+constexpr int kMaxLevinsonOrder = 32;
+
+// Choose lanes-per-frame K: the smallest power of two whose CTA span fits the shared-memory
+// budget, keeping each lane's part >= 2L samples.  Returns false if no fused configuration fits.
+bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, size_t* smem_bytes) {
+    const int sv = (int)(stride < (int64_t)n ? stride : n);
+    const int pad = ((sv & 1) == 0) ? 1 : 0;
+    const size_t budget_soft = 72 * 1024;  // 3 CTAs / SM
+    const size_t budget_hard = ctx->smem_optin;
+    int best_k = 0;
+    size_t best_bytes = 0;
+    for (int k = 1; k <= 32; k <<= 1) {
+        const int G = kThreads / k;
+        const int part = (n + k - 1) / k;
+        if (k > 1 && part < 2 * L) break;
+        const int64_t span = (int64_t)(G - 1) * sv + n;
+        const int64_t span_words = span + pad * (span / sv + 1) + 4;
+        const size_t stage_bytes = (size_t)G * (3 * L - 1) * sizeof(double);
+        size_t span_bytes = (size_t)span_words * sizeof(float);
+        span_bytes = (span_bytes + 15) & ~(size_t)15;
+        const size_t bytes = (size_t)n * sizeof(double) + (span_bytes > stage_bytes ? span_bytes : stage_bytes);
+        if (bytes > budget_hard) continue;
+        best_k = k;
+        best_bytes = bytes;
+        P->k = k;
+        P->frames_per_cta = G;
+        P->part = part;
+        P->span_words = (int)span_words;
+        if (bytes <= budget_soft) break;
+    }
+    if (!best_k) return false;
+    P->sv = sv;
+    P->pad = pad;
+    *smem_bytes = best_bytes;
+    return true;
+}
+
+template <typename TIn>
+int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_out, void* kc_out, int out_dtype,
+               bool do_levinson) {
+    static lpc_kernel_t table[kMaxFastLags + 1] = {nullptr};
+    static bool filled = false;
+    if (!filled) {
+        LpcTable<TIn, kMaxFastLags>::fill(table);
+        filled = true;
+    }
+    const double* win = nullptr;
+    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win);
+    if (st != VBX_OK) return st;
+
+    LpcParams P;
+    memset(&P, 0, sizeof(P));
+    size_t smem = 0;
+    const bool fused_ok = (L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem);
+    if (fused_ok) {
+        P.base = fr->base;
+        P.win = win;
+        P.r_out = r_out;
+        P.ac_out = ac_out;
+        P.kc_out = kc_out;
+        P.n_frames = fr->n_frames;
+        P.stride = fr->frame_stride;
+        P.seg_frames = vbx_frames_per_segment(fr);
+        P.seg_stride = fr->frames_per_segment > 0 ? fr->segment_stride : 0;
+        P.ctas_per_seg = (int)((P.seg_frames + P.frames_per_cta - 1) / P.frames_per_cta);
+        P.n = fr->frame_len;
+        P.out_f64 = (out_dtype == VBX_F64);
+        P.do_levinson = do_levinson ? 1 : 0;
+        lpc_kernel_t kern = table[L];
+        VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t grid = (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
+        VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P);
+        VBX_CHECK_LAUNCH(ctx, "lpc_fused_kernel");
+        return VBX_OK;
+    }
+
+    // fallback: generic autocorrelation (+ stand-alone Levinson through a scratch r buffer)
+    void* r_tmp = r_out;
+    int r_dtype = out_dtype;
+    if (do_levinson && (!r_out || out_dtype != VBX_F64)) {
+        st = vbx_arena_reserve(ctx, (size_t)fr->n_frames * L * sizeof(double));
+        if (st != VBX_OK) return st;
+        r_tmp = ctx->arena;
+        r_dtype = VBX_F64;
+    }
+    const size_t xs = (size_t)fr->frame_len * sizeof(double);
+    const int use_smem = xs <= ctx->smem_optin ? 1 : 0;
+    if (use_smem)
+        VBX_CUDA(ctx, cudaFuncSetAttribute(autocorr_generic_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs));
+    VBX_REQUIRE(ctx, fr->n_frames <= 0x7fffffffLL, "too many frames for one launch");
+    autocorr_generic_kernel<TIn><<<(unsigned)fr->n_frames, 256, use_smem ? xs : 0, ctx->stream>>>(
+        reinterpret_cast<const TIn*>(fr->base), win, fr->frame_stride, vbx_frames_per_segment(fr), fr->segment_stride,
+        fr->frame_len, L, r_tmp, r_dtype == VBX_F64, use_smem);
+    VBX_CHECK_LAUNCH(ctx, "autocorr_generic_kernel");
+    if (do_levinson) {
+        st = vbx_lpc_levinson(ctx, r_tmp, r_dtype, fr->n_frames, L, L - 1, ac_out, kc_out, out_dtype);
+        if (st != VBX_OK) return st;
+        if (r_out && r_tmp != r_out) {
+            // r was requested in f32 as well: convert with a second generic pass (rare path)
+            autocorr_generic_kernel<TIn><<<(unsigned)fr->n_frames, 256, use_smem ? xs : 0, ctx->stream>>>(
+                reinterpret_cast<const TIn*>(fr->base), win, fr->frame_stride, vbx_frames_per_segment(fr), fr->segment_stride,
+                fr->frame_len, L, r_out, 0, use_smem);
+            VBX_CHECK_LAUNCH(ctx, "autocorr_generic_kernel");
+        }
+    }
+    return VBX_OK;
+}
+
+int lpc_dispatch(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* ac_out, void* kc_out, int out_dtype,
+                 bool do_levinson) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, fr);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_lags >= 1, "n_lags must be >= 1");
+    VBX_REQUIRE(ctx, n_lags <= fr->frame_len, "n_lags (%d) > frame_len (%d): the reference's `self.len() - lag` underflows",
+                n_lags, fr->frame_len);
+    VBX_REQUIRE(ctx, !do_levinson || n_lags - 1 <= kMaxLevinsonOrder, "LPC order > %d not supported", kMaxLevinsonOrder);
+    if (fr->n_frames == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    if (fr->dtype == VBX_I16)
+        return launch_lpc<int16_t>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
+    return launch_lpc<float>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
+}
+
+// host twin: H2D the contiguous extent, run, D2H the outputs
+int lpc_host(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* ac_out, void* kc_out, int out_dtype,
+             bool do_levinson) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, fr);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    if (fr->n_frames == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    const size_t es = vbx_dtype_size(fr->dtype), os = vbx_dtype_size(out_dtype);
+    const size_t in_bytes = (size_t)vbx_frames_extent(fr) * es;
+    const size_t F = (size_t)fr->n_frames;
+    const size_t r_bytes = r_out ? F * n_lags * os : 0;
+    const size_t ac_bytes = (do_levinson && ac_out) ? F * n_lags * os : 0;
+    const size_t kc_bytes = (do_levinson && kc_out) ? F * (n_lags - 1) * os : 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // the fallback path may also use the arena for a scratch r: keep our block after that region
+    const size_t scratch = al(F * n_lags * sizeof(double));
+    st = vbx_arena_reserve(ctx, scratch + al(in_bytes) + al(r_bytes) + al(ac_bytes) + al(kc_bytes));
+    if (st != VBX_OK) return st;
+    char* p = (char*)ctx->arena + scratch;
+    void* d_in = p; p += al(in_bytes);
+    void* d_r = r_bytes ? p : nullptr; p += al(r_bytes);
+    void* d_ac = ac_bytes ? p : nullptr; p += al(ac_bytes);
+    void* d_kc = kc_bytes ? p : nullptr;
+    VBX_CUDA(ctx, cudaMemcpyAsync(d_in, fr->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    vbx_frames dfr = *fr;
+    dfr.base = d_in;
+    st = lpc_dispatch(ctx, &dfr, n_lags, d_r, d_ac, d_kc, out_dtype, do_levinson);
+    if (st != VBX_OK) return st;
+    if (r_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(r_out, d_r, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ac_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(ac_out, d_ac, ac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kc_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(kc_out, d_kc, kc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vbx_autocorrelate(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lags, void* r_out, int32_t out_dtype) {
+    if (ctx && !r_out && frames && frames->n_frames > 0) return vbx_fail(ctx, VBX_ERR_BADARG, "r_out is NULL");
+    return lpc_dispatch(ctx, frames, n_lags, r_out, nullptr, nullptr, out_dtype, false);
+}
+int vbx_autocorrelate_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lags, void* r_out, int32_t out_dtype) {
+    if (ctx && !r_out && frames && frames->n_frames > 0) return vbx_fail(ctx, VBX_ERR_BADARG, "r_out is NULL");
+    if (ctx && frames && n_lags < 1) return vbx_fail(ctx, VBX_ERR_BADARG, "n_lags must be >= 1");
+    return lpc_host(ctx, frames, n_lags, r_out, nullptr, nullptr, out_dtype, false);
+}
+
+int vbx_lpc(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out, int32_t out_dtype) {
+    if (ctx && p < 1) return vbx_fail(ctx, VBX_ERR_BADARG, "LPC order must be >= 1");
+    return lpc_dispatch(ctx, frames, p + 1, r_out, ac_out, kc_out, out_dtype, true);
+}
+int vbx_lpc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out,
+                 int32_t out_dtype) {
+    if (ctx && p < 1) return vbx_fail(ctx, VBX_ERR_BADARG, "LPC order must be >= 1");
+    if (ctx && frames && p + 1 > frames->frame_len) return vbx_fail(ctx, VBX_ERR_BADARG, "order + 1 > frame_len");
+    return lpc_host(ctx, frames, p + 1, r_out, ac_out, kc_out, out_dtype, true);
+}
+
+int vbx_lpc_levinson(vbx_ctx* ctx, const void* r, int32_t r_dtype, int64_t n_frames, int32_t r_stride, int32_t p,
+                     void* ac_out, void* kc_out, int32_t out_dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    static lev_kernel_t table[kMaxLevinsonOrder + 1] = {nullptr};
+    static bool filled = false;
+    if (!filled) {
+        LevTable<kMaxLevinsonOrder>::fill(table);
+        filled = true;
+    }
+    VBX_REQUIRE(ctx, p >= 1 && p <= kMaxLevinsonOrder, "LPC order must be in 1..%d", kMaxLevinsonOrder);
+    VBX_REQUIRE(ctx, r_stride >= p + 1, "r_stride must be >= p + 1 (lpc_mut reads self[0..=p])");
+    VBX_REQUIRE(ctx, r_dtype == VBX_F32 || r_dtype == VBX_F64, "r_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_frames >= 0, "n_frames < 0");
+    if (n_frames == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, r != nullptr, "r is NULL");
+    cudaSetDevice(ctx->device);
+    const int64_t grid = (n_frames + 127) / 128;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+    table[p]<<<(unsigned)grid, 128, 0, ctx->stream>>>(r, r_dtype == VBX_F64, n_frames, r_stride, ac_out, kc_out,
+                                                      out_dtype == VBX_F64);
+    VBX_CHECK_LAUNCH(ctx, "levinson_kernel");
+    return VBX_OK;
+}
+
+}  // extern "C"
