@@ -13,11 +13,13 @@
 // 1 LDS (sample) + 1 LDS.64 (window) + 1 DMUL + L DFMA, no cross-lane traffic in the loop.  K>1
 // partial sums are combined with shuffles; Levinson then runs one thread per frame out of shared
 // memory and the results leave through a coalesced store.
+#include <cstdlib>
+
 #include "vbx_internal.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kMaxThreads = 128;
 
 struct LpcParams {
     const void* base;      // samples
@@ -30,6 +32,8 @@ struct LpcParams {
     int64_t seg_frames;    // frames per segment (utterance); CTAs never straddle segments
     int64_t seg_stride;    // samples between segment starts
     int ctas_per_seg;
+    int threads;           // CTA size (multiple of 32, <= kMaxThreads)
+    unsigned sv_magic;     // floor(2^32 / sv) + 1: s / sv == __umulhi(s, sv_magic) for s·sv < 2^32
     int n;                 // frame length
     int k;                 // lanes per frame (power of two <= 32)
     int frames_per_cta;    // G = kThreads / k
@@ -73,7 +77,7 @@ __device__ __forceinline__ void levinson(const double* __restrict__ r, double* _
 }
 
 template <int L, typename TIn>
-__global__ void __launch_bounds__(kThreads) lpc_fused_kernel(const LpcParams P) {
+__global__ void __launch_bounds__(kMaxThreads, (L <= 13 ? 5 : 1)) lpc_fused_kernel(const LpcParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_win = reinterpret_cast<double*>(smem_raw);                 // [n]
     float* s_span = reinterpret_cast<float*>(s_win + P.n);               // padded span
@@ -89,21 +93,66 @@ __global__ void __launch_bounds__(kThreads) lpc_fused_kernel(const LpcParams P) 
     const TIn* __restrict__ base = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride;
 
     // ---- stage window + span -------------------------------------------------------------
-    for (int i = tid; i < n; i += kThreads) s_win[i] = __ldg(P.win + i);
+    const int nthreads = P.threads;
+    for (int i = tid; i < n; i += nthreads) s_win[i] = __ldg(P.win + i);
     if (P.stride <= (int64_t)n) {
-        // overlapped / packed frames: one contiguous run of (Gc-1)·stride + n samples
+        // overlapped / packed frames: one contiguous run of (Gc-1)·stride + n samples, copied with many
+        // independent loads in flight per thread; word s lands at s + pad·(s / sv)
         const TIn* src = base + j0 * P.stride;
         const int total = (Gc - 1) * sv + n;
-        const int nblk = (total + sv - 1) / sv;
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int b = warp; b < nblk; b += kThreads / 32) {
-            const int lo = b * sv, cnt = min(sv, total - lo);
-            for (int j = lane; j < cnt; j += 32) s_span[lo + j + pad * b] = vbx_load_sample<TIn>(src + lo + j);
+        const unsigned magic = P.sv_magic;
+        auto phys = [&](int s_) -> int { return pad ? s_ + (int)__umulhi((unsigned)s_, magic) : s_; };
+        int done = 0;
+        if (sizeof(TIn) == 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            // 16-byte loads, 8 in flight per thread.  With pad == 0 the copy is the identity; with
+            // sv % 4 == 0 the four words of a load stay inside one sv-block (one division per load)
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            const int n4 = total >> 2;
+            for (int v0 = tid; v0 < n4; v0 += 8 * nthreads) {
+                float4 a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int v = v0 + u * nthreads;
+                    if (v < n4) a[u] = __ldg(src4 + v);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int v = v0 + u * nthreads;
+                    if (v < n4) {
+                        if (pad == 0 || (sv & 3) == 0) {
+                            float* dst = s_span + phys(4 * v);
+                            dst[0] = a[u].x;
+                            dst[1] = a[u].y;
+                            dst[2] = a[u].z;
+                            dst[3] = a[u].w;
+                        } else {
+                            s_span[phys(4 * v)] = a[u].x;
+                            s_span[phys(4 * v + 1)] = a[u].y;
+                            s_span[phys(4 * v + 2)] = a[u].z;
+                            s_span[phys(4 * v + 3)] = a[u].w;
+                        }
+                    }
+                }
+            }
+            done = n4 << 2;
+        }
+        for (int s0 = done + tid; s0 < total; s0 += 8 * nthreads) {
+            float a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s_ = s0 + u * nthreads;
+                if (s_ < total) a[u] = vbx_load_sample<TIn>(src + s_);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s_ = s0 + u * nthreads;
+                if (s_ < total) s_span[phys(s_)] = a[u];
+            }
         }
     } else {
         // gapped frames: each frame's n samples land in consecutive blocks of sv == n words
         const int warp = tid >> 5, lane = tid & 31;
-        for (int g = warp; g < Gc; g += kThreads / 32) {
+        for (int g = warp; g < Gc; g += nthreads / 32) {
             const TIn* src = base + (j0 + g) * P.stride;
             for (int j = lane; j < n; j += 32) s_span[g * (sv + pad) + j] = vbx_load_sample<TIn>(src + j);
         }
@@ -136,11 +185,27 @@ __global__ void __launch_bounds__(kThreads) lpc_fused_kernel(const LpcParams P) 
 #pragma unroll
             for (int j = 1; j < L; ++j) { h[j] = fetch(i); ++i; }
         }
-        // full chunks of L samples: ring slot u holds xw[i+u]; lag products use static slots
+        // full chunks of L samples: ring slot u holds xw[i+u]; lag products use static slots.  A chunk
+        // that contains no pad word reads its samples at immediate offsets (no per-sample bookkeeping).
+        if (pad == 0) left = 0x3fffffff;
         for (; i + L <= i_end; i += L) {
+            float xf[L];
+            if (left > L) {
+#pragma unroll
+                for (int u = 0; u < L; ++u) xf[u] = s_span[pos + u];
+                pos += L;
+                left -= L;
+            } else {
+#pragma unroll
+                for (int u = 0; u < L; ++u) {
+                    xf[u] = s_span[pos];
+                    ++pos;
+                    if (--left == 0) { pos += pad; left = sv; }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < L; ++u) {
-                const double xn = fetch(i + u);
+                const double xn = (double)xf[u] * s_win[i + u];
                 h[u] = xn;
 #pragma unroll
                 for (int lag = 0; lag < L; ++lag) acc[lag] = fma(xn, h[(u - lag + L) % L], acc[lag]);
@@ -204,10 +269,10 @@ __global__ void __launch_bounds__(kThreads) lpc_fused_kernel(const LpcParams P) 
         const int64_t off = g0 * per_frame;
         if (P.out_f64) {
             double* o = reinterpret_cast<double*>(out) + off;
-            for (int idx = tid; idx < total; idx += kThreads) o[idx] = src[idx];
+            for (int idx = tid; idx < total; idx += nthreads) o[idx] = src[idx];
         } else {
             float* o = reinterpret_cast<float*>(out) + off;
-            for (int idx = tid; idx < total; idx += kThreads) o[idx] = (float)src[idx];
+            for (int idx = tid; idx < total; idx += nthreads) o[idx] = (float)src[idx];
         }
     };
     store(P.r_out, s_r, L);
@@ -303,20 +368,31 @@ template <> struct LevTable<0> {
 };
 constexpr int kMaxLevinsonOrder = 32;
 
-// Choose lanes-per-frame K: the smallest power of two whose CTA span fits the shared-memory
-// budget, keeping each lane's part >= 2L samples.  Returns false if no fused configuration fits.
+// Choose lanes-per-frame K (and the CTA size): the smallest power of two whose CTA span fits the
+// shared-memory budget, keeping each lane's part >= 2L samples.  Returns false if no fused
+// configuration fits.  VBX_LPC_PLAN="k:threads" overrides the choice (tuning experiments).
 bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, size_t* smem_bytes) {
     const int sv = (int)(stride < (int64_t)n ? stride : n);
     const int pad = ((sv & 1) == 0) ? 1 : 0;
     const size_t budget_soft = 72 * 1024;  // 3 CTAs / SM
     const size_t budget_hard = ctx->smem_optin;
+    int threads = kMaxThreads, force_k = 0;
+    if (const char* e = getenv("VBX_LPC_PLAN")) {
+        int a = 0, b = 0;
+        if (sscanf(e, "%d:%d", &a, &b) == 2 && a >= 1 && a <= 32 && (a & (a - 1)) == 0 && b >= 32 && b <= kMaxThreads && b % 32 == 0) {
+            force_k = a;
+            threads = b;
+        }
+    }
     int best_k = 0;
     size_t best_bytes = 0;
     for (int k = 1; k <= 32; k <<= 1) {
-        const int G = kThreads / k;
+        if (force_k && k != force_k) continue;
+        const int G = threads / k;
         const int part = (n + k - 1) / k;
         if (k > 1 && part < 2 * L) break;
         const int64_t span = (int64_t)(G - 1) * sv + n;
+        if (span * (int64_t)sv >= (1LL << 32)) continue;  // sv_magic validity
         const int64_t span_words = span + pad * (span / sv + 1) + 4;
         const size_t stage_bytes = (size_t)G * (3 * L - 1) * sizeof(double);
         size_t span_bytes = (size_t)span_words * sizeof(float);
@@ -334,6 +410,8 @@ bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, 
     if (!best_k) return false;
     P->sv = sv;
     P->pad = pad;
+    P->threads = threads;
+    P->sv_magic = sv > 1 ? (unsigned)((1ULL << 32) / (unsigned)sv) + 1u : 0u;
     *smem_bytes = best_bytes;
     return true;
 }
@@ -373,7 +451,7 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
         VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
-        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P);
+        kern<<<(unsigned)grid, P.threads, smem, ctx->stream>>>(P);
         VBX_CHECK_LAUNCH(ctx, "lpc_fused_kernel");
         return VBX_OK;
     }
