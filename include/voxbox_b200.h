@@ -148,6 +148,80 @@ VBX_API int vbx_lpc(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_o
 VBX_API int vbx_lpc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out,
                          int32_t out_dtype);
 
+/* ---- spectrum.rs:94-146  LPC::{lpc_praat_mut, lpc_praat} (Burg, Praat form) ---------------------- */
+/* coeffs_out: [F][p] (no leading 1, sign as the reference returns them).  status_out[f] (optional) =
+ * VBX_ERR_LPC where the reference returns Err(LPC("Denum was <= 0.0")); such frames get NaN coefficients. */
+VBX_API int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs_out, uint8_t* status_out,
+                         int32_t out_dtype);
+
+/* ---- polynomial.rs:10-205  Polynomial on [Complex<T>] ------------------------------------------------ */
+/* Complex arrays are interleaved (re, im) of `dtype` (VBX_F32|VBX_F64), `len` coefficients per polynomial in
+ * ascending powers, len <= 64.  One polynomial per batch entry. */
+/* find_roots_mut (:92-152): roots_out[f][0..len) = the buffer after the reference's write-back (roots in the
+ * reference's order, then zeros).  status_out[f] = VBX_ERR_POLYNOMIAL for "Zero degree polynomial" /
+ * "Failed to find roots" (roots_out then holds the input), VBX_ERR_BADARG where the reference panics (off_low > 0). */
+VBX_API int vbx_find_roots(vbx_ctx* ctx, const void* coeffs, int32_t dtype, int64_t n_polys, int32_t len, void* roots_out,
+                           uint8_t* status_out);
+VBX_API int64_t vbx_find_roots_work_size(int64_t len); /* polynomial.rs:75-77 (the library needs no caller workspace) */
+/* laguerre (:34-72): z_out[f] = one Laguerre solve from `start`, n = len-1. */
+VBX_API int vbx_laguerre(vbx_ctx* ctx, const void* coeffs, int32_t dtype, int64_t n_polys, int32_t len, double start_re,
+                         double start_im, void* z_out);
+/* div_polynomial_mut (:155-195): coeffs_inout /= (x + other); remainder to rem_out (optional, len entries).
+ * `other`: one complex value, or one per polynomial if other_per_poly != 0.  other == 0 -> VBX_ERR_POLYNOMIAL. */
+VBX_API int vbx_div_polynomial(vbx_ctx* ctx, void* coeffs_inout, int32_t dtype, int64_t n_polys, int32_t len,
+                               const void* other, int32_t other_per_poly, void* rem_out, uint8_t* status_out);
+
+/* ---- spectrum.rs:149-210  Resonance::from_root, ToResonance::to_resonance ----------------------------------- */
+/* roots: [F][n_roots] complex.  res_out: [F][res_slots] resonance pairs of out_dtype, ascending frequency,
+ * zero padded; nres_out[f] (optional) = count.  strict_im = 0: to_resonance (roots with im >= 0);
+ * strict_im = 1: find_formants' filter (im > 0, lib.rs:95).  50 Hz guard band as the reference. */
+VBX_API int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dtype, int64_t n_frames, int32_t n_roots,
+                                    double sample_rate, int32_t strict_im, void* res_out, int32_t res_slots,
+                                    int32_t* nres_out, int32_t out_dtype);
+
+/* LPC coefficients -> roots -> resonances in one kernel (the K3+K4 stage of find_formants).
+ * lpc: [F][lpc_stride], either [1, a1..ap] (lpc_has_leading_one = 1, Levinson's `ac`) or [a1..ap] (Burg).
+ * precision: 0 = fp32 Laguerre/deflation + fp64 Newton polish on the original polynomial (default), 1 = fp64
+ * Laguerre/deflation as the reference's f64 instantiation, -1 = library default (env VBX_ROOTS_F64=1 selects 1).
+ * roots_out (optional): [F][p] complex roots in find_roots order.  status_in (optional): frames whose LPC stage
+ * failed are passed through with zero resonances. */
+VBX_API int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride,
+                                  int32_t p, int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im,
+                                  const uint8_t* status_in, void* res_out, int32_t res_slots, int32_t* nres_out,
+                                  void* roots_out, uint8_t* status_out, int32_t out_dtype, int32_t precision);
+
+/* ---- spectrum.rs:216-369  EstimateFormants::estimate_formants + FormantExtractor ------------------------------ */
+/* Runs the McCandless step over frames, sequentially inside each segment (utterance), segments in parallel.
+ * resonances: [n_segments*frames_per_segment][res_slots] pairs of res_dtype; the step sees the first
+ * n_resonances entries of each frame (entries beyond res_slots read as (0,0): find_formants passes 32 zero-padded
+ * slots, lib.rs:114).  est_inout: [n_segments][n_estimates] pairs of dtype: starting estimates in, final state out.
+ * tracks_out (optional): [F][n_estimates] = the estimates after each frame (FormantExtractor::next).
+ * status_in (optional): frames with a non-zero status leave the estimates untouched. */
+VBX_API int vbx_estimate_formants(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots,
+                                  int32_t n_resonances, int64_t n_segments, int64_t frames_per_segment,
+                                  const uint8_t* status_in, void* est_inout, int32_t n_estimates, void* tracks_out,
+                                  int32_t dtype);
+
+/* ---- lib.rs:26-116  find_formants (+ work-size helpers) -------------------------------------------------------- */
+typedef enum vbx_lpc_method {
+    VBX_LPC_BURG = 0,    /* lpc_praat_mut on the windowed frame: the reference's find_formants (use HANN_PERIODIC) */
+    VBX_LPC_AUTOCORR = 1 /* autocorrelate(p+1) -> lpc(p): the north-star "LPC-12 + formant" chain (HANN_SYMMETRIC) */
+} vbx_lpc_method;
+VBX_API int64_t vbx_find_formants_real_work_size(int64_t buf_len, int64_t n_coeffs); /* lib.rs:30-32 */
+VBX_API int64_t vbx_find_formants_complex_work_size(int64_t n_coeffs);               /* lib.rs:34-36 */
+/* One call = find_formants applied to every frame of the view, in order, inside each segment (utterance):
+ * window -> LPC -> roots -> resonances (im > 0, sorted, zero padded to 32) -> estimate_formants.
+ * resample_ratio is 1 (the linear resampler of lib.rs:57-61 is not on this path yet).
+ * est_inout [n_segments][n_formants] pairs (state in/out); tracks_out [F][n_formants] (optional);
+ * resonances_out [F][32] pairs (optional); nres_out [F] (optional); status_out [F] (optional):
+ * VBX_ERR_LPC frames leave the state untouched, exactly as the reference returns Err before the tracker. */
+VBX_API int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
+                              int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
+                              void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
+VBX_API int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
+                                   int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
+                                   void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
+
 #ifdef __cplusplus
 }
 #endif

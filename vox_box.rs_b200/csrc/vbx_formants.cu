@@ -1,0 +1,850 @@
+// vbx_formants.cu — the formant path: Burg LPC, polynomial roots, resonances, McCandless tracker.
+//
+// Replaces, batched over frames / utterances:
+//   spectrum.rs:94-146    LPC::{lpc_praat_mut, lpc_praat}        (Burg, Praat NUMburg form)
+//   polynomial.rs:10-205  Polynomial::{laguerre, find_roots(_mut), div_polynomial(_mut), degree, off_low}
+//   spectrum.rs:149-210   Resonance::from_root, ToResonance::to_resonance
+//   spectrum.rs:216-369   EstimateFormants::estimate_formants, FormantExtractor
+//   lib.rs:26-116         find_formants (+ work-size helpers)
+//
+// Kernel shapes (DESIGN.md §K2b–K5):
+//   burg_warp_kernel<C>   one warp per frame; the forward/backward error vectors live in registers
+//                         (C consecutive elements per lane), fp64; one neighbour shuffle per order.
+//   lpc_roots_kernel<P>   one thread per frame; the polynomial lives in registers; Laguerre + forward
+//                         deflation in fp32 (or fp64), fp64 Newton polish on the original polynomial,
+//                         resonances computed and rank-sorted in fp64.
+//   tracker_kernel        one thread per utterance, sequential over its frames (McCandless step).
+#include <cstdlib>
+
+#include "vbx_complex.cuh"
+#include "vbx_internal.cuh"
+#include "vbx_roots_kernel.cuh"
+
+namespace {
+
+// =============================================================================================
+// Burg
+// =============================================================================================
+struct BurgParams {
+    const void* base;
+    const double* win;
+    void* coeffs_out;      // [F][p]
+    uint8_t* status_out;   // [F] or null
+    int64_t n_frames, stride, seg_frames, seg_stride;
+    int n, p, out_f64;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += vbx_shfl_xor(v, m);
+    return v;
+}
+
+// spectrum.rs:116-140.  b1[j] = x[j], b2[j] = x[j+1] for j in [0, n−1); lane ℓ owns j in [ℓC, ℓC+C).
+template <int C, typename TIn>
+__global__ void __launch_bounds__(128) burg_warp_kernel(const BurgParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= P.n_frames) return;
+    const int64_t seg = f / P.seg_frames;
+    const TIn* __restrict__ x = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride + (f - seg * P.seg_frames) * P.stride;
+    const int n = P.n, p = P.p;
+    const int j0 = lane * C;
+    double b1[C], b2[C];
+    {
+        // xw[j0 .. j0+C] (C+1 values): b1[c] = xw[j0+c], b2[c] = xw[j0+c+1]; entries j >= n−1 are zero
+        double prev = (j0 < n) ? (double)vbx_load_sample<TIn>(x + j0) * __ldg(P.win + j0) : 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + c + 1;
+            const double nxt = (j < n) ? (double)vbx_load_sample<TIn>(x + j) * __ldg(P.win + j) : 0.0;
+            const bool valid = (j0 + c) < n - 1;
+            b1[c] = valid ? prev : 0.0;
+            b2[c] = valid ? nxt : 0.0;
+            prev = nxt;
+        }
+    }
+    double co[32], aa[32];  // p <= 32; indexed with lane-uniform runtime indices (local memory, tiny)
+    int status = VBX_OK;
+    for (int i = 1; i <= p; ++i) {
+        // num = Σ b1·b2, denum = Σ b1² + b2² over j < n − i
+        const int m = (n - i) - j0;  // this lane's elements c < m take part
+        double num0 = 0.0, num1 = 0.0, den0 = 0.0, den1 = 0.0, den2 = 0.0, den3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (c < m) {
+                if (c & 1) {
+                    num1 = fma(b1[c], b2[c], num1);
+                    den1 = fma(b1[c], b1[c], den1);
+                    den3 = fma(b2[c], b2[c], den3);
+                } else {
+                    num0 = fma(b1[c], b2[c], num0);
+                    den0 = fma(b1[c], b1[c], den0);
+                    den2 = fma(b2[c], b2[c], den2);
+                }
+            }
+        }
+        const double num = warp_sum(num0 + num1);
+        const double denum = warp_sum((den0 + den1) + (den2 + den3));
+        if (!(denum > 0.0)) {  // `denum <= 0` ⇒ Err(LPC("Denum was <= 0.0")); NaN falls through in the reference
+            if (denum <= 0.0) { status = VBX_ERR_LPC; break; }
+        }
+        const double k = 2.0 * num / denum;
+        co[i - 1] = k;
+        for (int j = 1; j < i; ++j) co[j - 1] = aa[j - 1] - k * aa[i - j - 1];
+        if (i < p) {
+            for (int j = 1; j <= i; ++j) aa[j - 1] = co[j - 1];
+            const double a = aa[i - 1];
+            // b1[j] −= a·b2[j]; b2[j] = b2[j+1] − a·b1[j+1] (old values), j < n − i − 1
+            const double nb1 = __shfl_down_sync(0xffffffffu, b1[0], 1);
+            const double nb2 = __shfl_down_sync(0xffffffffu, b2[0], 1);
+            const double e1 = (lane == 31) ? 0.0 : nb1, e2 = (lane == 31) ? 0.0 : nb2;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double o1 = b1[c], o2 = b2[c];
+                const double n1 = (c + 1 < C) ? b1[c + 1] : e1;
+                const double n2 = (c + 1 < C) ? b2[c + 1] : e2;
+                b1[c] = fma(-a, o2, o1);
+                b2[c] = fma(-a, n1, n2);
+            }
+        }
+    }
+    if (lane == 0) {
+        if (P.status_out) P.status_out[f] = (uint8_t)status;
+        for (int j = 0; j < p; ++j) {
+            const double v = (status == VBX_OK) ? -co[j] : nan("");
+            if (P.out_f64) reinterpret_cast<double*>(P.coeffs_out)[f * p + j] = v;
+            else reinterpret_cast<float*>(P.coeffs_out)[f * p + j] = (float)v;
+        }
+    }
+}
+
+// Any frame length: one CTA per frame, b1/b2 in shared memory (or a global scratch when too long).
+template <typename TIn>
+__global__ void __launch_bounds__(256) burg_block_kernel(const BurgParams P, double* scratch, int use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[2][8];
+    __shared__ double s_co[32], s_aa[32];
+    __shared__ int s_status;
+    const int64_t f = blockIdx.x;
+    const int64_t seg = f / P.seg_frames;
+    const TIn* __restrict__ x = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride + (f - seg * P.seg_frames) * P.stride;
+    const int n = P.n, p = P.p, tid = threadIdx.x, T = blockDim.x;
+    double* b1 = use_smem ? reinterpret_cast<double*>(smem_raw) : scratch + (size_t)f * 2 * n;
+    double* b2 = b1 + n;
+    for (int j = tid; j < n - 1; j += T) {
+        b1[j] = (double)vbx_load_sample<TIn>(x + j) * __ldg(P.win + j);
+        b2[j] = (double)vbx_load_sample<TIn>(x + j + 1) * __ldg(P.win + j + 1);
+    }
+    if (tid == 0) s_status = VBX_OK;
+    __syncthreads();
+    for (int i = 1; i <= p; ++i) {
+        double num = 0.0, den = 0.0;
+        for (int j = tid; j < n - i; j += T) {
+            num = fma(b1[j], b2[j], num);
+            den = fma(b1[j], b1[j], den);
+            den = fma(b2[j], b2[j], den);
+        }
+        num = warp_sum(num);
+        den = warp_sum(den);
+        if ((tid & 31) == 0) { s_red[0][tid >> 5] = num; s_red[1][tid >> 5] = den; }
+        __syncthreads();
+        if (tid == 0) {
+            double sn = 0.0, sd = 0.0;
+            for (int w = 0; w < (T >> 5); ++w) { sn += s_red[0][w]; sd += s_red[1][w]; }
+            if (sd <= 0.0) s_status = VBX_ERR_LPC;
+            else {
+                const double k = 2.0 * sn / sd;
+                s_co[i - 1] = k;
+                for (int j = 1; j < i; ++j) s_co[j - 1] = s_aa[j - 1] - k * s_aa[i - j - 1];
+                if (i < p) for (int j = 1; j <= i; ++j) s_aa[j - 1] = s_co[j - 1];
+            }
+        }
+        __syncthreads();
+        if (s_status != VBX_OK) break;
+        if (i < p) {
+            const double a = s_aa[i - 1];
+            for (int t0 = 0; t0 < n - i - 1; t0 += T) {
+                const int j = t0 + tid;
+                double v1 = 0.0, v2 = 0.0;
+                const bool act = j < n - i - 1;
+                if (act) { v1 = fma(-a, b2[j], b1[j]); v2 = fma(-a, b1[j + 1], b2[j + 1]); }
+                __syncthreads();
+                if (act) { b1[j] = v1; b2[j] = v2; }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        const int status = s_status;
+        if (P.status_out) P.status_out[f] = (uint8_t)status;
+        for (int j = 0; j < p; ++j) {
+            const double v = (status == VBX_OK) ? -s_co[j] : nan("");
+            if (P.out_f64) reinterpret_cast<double*>(P.coeffs_out)[f * p + j] = v;
+            else reinterpret_cast<float*>(P.coeffs_out)[f * p + j] = (float)v;
+        }
+    }
+}
+
+typedef void (*burg_kernel_t)(const BurgParams);
+template <typename TIn> burg_kernel_t pick_burg(int c_needed, int* c_out) {
+#define VBX_BURG_CASE(CC) if (c_needed <= CC) { *c_out = CC; return burg_warp_kernel<CC, TIn>; }
+    VBX_BURG_CASE(4) VBX_BURG_CASE(8) VBX_BURG_CASE(13) VBX_BURG_CASE(16) VBX_BURG_CASE(20) VBX_BURG_CASE(26)
+    VBX_BURG_CASE(32) VBX_BURG_CASE(36)
+#undef VBX_BURG_CASE
+    *c_out = 0;
+    return nullptr;
+}
+
+template <typename TIn>
+int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uint8_t* status_out, int out_dtype) {
+    const double* win = nullptr;
+    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win);
+    if (st != VBX_OK) return st;
+    BurgParams P;
+    P.base = fr->base; P.win = win; P.coeffs_out = coeffs_out; P.status_out = status_out;
+    P.n_frames = fr->n_frames; P.stride = fr->frame_stride;
+    P.seg_frames = vbx_frames_per_segment(fr);
+    P.seg_stride = fr->frames_per_segment > 0 ? fr->segment_stride : 0;
+    P.n = fr->frame_len; P.p = p; P.out_f64 = (out_dtype == VBX_F64);
+    int C = 0;
+    burg_kernel_t kern = pick_burg<TIn>((fr->frame_len - 1 + 31) / 32, &C);
+    if (kern && !getenv("VBX_BURG_FORCE_BLOCK")) {
+        const int warps = 4;
+        const int64_t grid = (fr->n_frames + warps - 1) / warps;
+        VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+        kern<<<(unsigned)grid, warps * 32, 0, ctx->stream>>>(P);
+        VBX_CHECK_LAUNCH(ctx, "burg_warp_kernel");
+        return VBX_OK;
+    }
+    const size_t need = (size_t)2 * fr->frame_len * sizeof(double);
+    const int use_smem = need <= ctx->smem_optin - 1024 ? 1 : 0;
+    double* scratch = nullptr;
+    if (!use_smem) {
+        st = vbx_arena_reserve(ctx, need * (size_t)fr->n_frames);
+        if (st != VBX_OK) return st;
+        scratch = reinterpret_cast<double*>(ctx->arena);
+    } else {
+        VBX_CUDA(ctx, cudaFuncSetAttribute(burg_block_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    }
+    VBX_REQUIRE(ctx, fr->n_frames <= 0x7fffffffLL, "too many frames for one launch");
+    burg_block_kernel<TIn><<<(unsigned)fr->n_frames, 256, use_smem ? need : 0, ctx->stream>>>(P, scratch, use_smem);
+    VBX_CHECK_LAUNCH(ctx, "burg_block_kernel");
+    return VBX_OK;
+}
+
+// =============================================================================================
+// roots → resonances
+// =============================================================================================
+using namespace vbx_roots;
+
+int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*0 fast f32+polish, 1 f64*/) {
+    static roots_kernel_t tf[kMaxRootsOrder + 1] = {nullptr}, td[kMaxRootsOrder + 1] = {nullptr};
+    static bool filled = false;
+    if (!filled) {
+        fill_f32_lo(tf); fill_f32_hi(tf);
+        fill_f64_lo(td); fill_f64_hi(td);
+        filled = true;
+    }
+    VBX_REQUIRE(ctx, p >= 2 && p <= kMaxRootsOrder, "LPC order for root finding must be in 2..%d", kMaxRootsOrder);
+    const int64_t grid = (Q.n_frames + 127) / 128;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+    (precision == 1 ? td : tf)[p]<<<(unsigned)grid, 128, 0, ctx->stream>>>(Q);
+    VBX_CHECK_LAUNCH(ctx, "lpc_roots_kernel");
+    return VBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic Polynomial::find_roots_mut / laguerre / div_polynomial_mut on complex coefficient arrays
+// (any content, len <= 64): one thread per polynomial, arrays in local memory, the reference's own
+// control flow incl. degree()/off_low() handling (polynomial.rs:92-152).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPolyLen = 64;
+
+template <typename T> __device__ inline bool cx_is_zero(vcx<T> a) { return a.re == (T)0 && a.im == (T)0; }
+template <typename T> __device__ inline int poly_degree_dev(const vcx<T>* c, int len) {
+    for (int i = len - 1; i >= 0; --i)
+        if (!cx_is_zero(c[i])) return i;
+    return 0;
+}
+template <typename T> __device__ inline int poly_off_low_dev(const vcx<T>* c, int len) {
+    for (int i = 0; i < len; ++i)
+        if (!cx_is_zero(c[i])) return i;
+    return 0;
+}
+// polynomial.rs:155-195
+template <typename T> __device__ inline int div_polynomial_dev(vcx<T>* self, int len, vcx<T> other, vcx<T>* rem) {
+    for (int i = 0; i < len; ++i) rem[i] = self[i];
+    if (cx_is_zero(other)) return VBX_ERR_POLYNOMIAL;  // "Tried to divide by zero"
+    const int ns = poly_degree_dev(self, len);
+    if (ns < 1) return VBX_ERR_BADARG;  // (0..(ns − 1 + 1)).rev() with ns == 0: `ns - ds` underflows in the reference
+    for (int i = ns - 1; i >= 0; --i) {
+        self[i] = rem[i + 1];
+        rem[i] = csub(rem[i], cmul(self[i], other));
+    }
+    for (int k = 1; k < ns + 1; ++k) rem[poly_degree_dev(rem, len)] = cmk<T>((T)0, (T)0);
+    const int l = poly_degree_dev(self, len);
+    const int cnt = (l + 1) - ns - 1 + 1;
+    if (cnt < 0) return VBX_ERR_BADARG;
+    for (int k = 0; k < cnt; ++k) self[poly_degree_dev(self, len)] = cmk<T>((T)0, (T)0);
+    return VBX_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) find_roots_generic_kernel(const T* __restrict__ coeffs, int64_t n_polys, int len,
+                                                                T* roots_out, uint8_t* status_out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_polys) return;
+    vcx<T> self[kMaxPolyLen], c[kMaxPolyLen], rem[kMaxPolyLen], zr[kMaxPolyLen + 1];
+    for (int i = 0; i < len; ++i) self[i] = cmk<T>(coeffs[((size_t)f * len + i) * 2], coeffs[((size_t)f * len + i) * 2 + 1]);
+    for (int i = 0; i <= len; ++i) zr[i] = cmk<T>((T)0, (T)0);
+    int status = VBX_OK;
+    const int hi = poly_degree_dev(self, len);
+    int zi = 0;
+    if (hi < 1) status = VBX_ERR_POLYNOMIAL;  // "Zero degree polynomial: no roots to be found."
+    else {
+        const int lo = poly_off_low_dev(self, len);
+        int m = hi - lo;
+        const int clen = hi - lo + 1;
+        for (int i = 0; i < lo; ++i) { zr[i] = cmk<T>((T)0, (T)0); ++zi; }
+        if (lo > 0) status = VBX_ERR_BADARG;  // polynomial.rs:110-112 indexes un-shifted ⇒ the reference panics
+        else {
+            for (int i = 0; i < clen; ++i) c[i] = self[i];
+            for (int k = m; k >= 3 && status == VBX_OK; --k) {
+                const vcx<T> z = laguerre_solve_rt<T>(c, clen, cmk<T>((T)-2, (T)-2));
+                zr[zi++] = z;
+                if (div_polynomial_dev<T>(c, clen, cneg(z), rem) != VBX_OK) status = VBX_ERR_POLYNOMIAL;  // "Failed to find roots"
+                m = m - 1;
+            }
+            if (status == VBX_OK && m == 2) {
+                const vcx<T> a2 = cadd(c[2], c[2]);
+                const vcx<T> d = csqrt_principal(csub(cmul(c[1], c[1]), cmul(cmul(cmk<T>((T)4, (T)0), c[2]), c[0])));
+                const vcx<T> x = cneg(c[1]);
+                zr[zi] = cdiv(cadd(x, d), a2);
+                zr[zi + 1] = cdiv(csub(x, d), a2);
+                zi += 2;
+            }
+            if (status == VBX_OK && m == 1) { zr[zi] = cdiv(cneg(c[0]), c[1]); zi += 1; }
+        }
+    }
+    if (status_out) status_out[f] = (uint8_t)status;
+    // write-back: roots, one extra (zero) element, rest zero (polynomial.rs:145-150); on error the input is kept
+    for (int i = 0; i < len; ++i) {
+        vcx<T> v = (status == VBX_OK) ? ((i <= zi) ? zr[i] : cmk<T>((T)0, (T)0)) : self[i];
+        roots_out[((size_t)f * len + i) * 2] = v.re;
+        roots_out[((size_t)f * len + i) * 2 + 1] = v.im;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) laguerre_generic_kernel(const T* __restrict__ coeffs, int64_t n_polys, int len, T sre,
+                                                              T sim, T* z_out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_polys) return;
+    vcx<T> c[kMaxPolyLen];
+    for (int i = 0; i < len; ++i) c[i] = cmk<T>(coeffs[((size_t)f * len + i) * 2], coeffs[((size_t)f * len + i) * 2 + 1]);
+    const vcx<T> z = laguerre_solve_rt<T>(c, len, cmk<T>(sre, sim));
+    z_out[f * 2] = z.re;
+    z_out[f * 2 + 1] = z.im;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) div_polynomial_generic_kernel(T* coeffs, int64_t n_polys, int len, const T* __restrict__ other,
+                                                                    int other_per_poly, T* rem_out, uint8_t* status_out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_polys) return;
+    vcx<T> self[kMaxPolyLen], rem[kMaxPolyLen];
+    for (int i = 0; i < len; ++i) self[i] = cmk<T>(coeffs[((size_t)f * len + i) * 2], coeffs[((size_t)f * len + i) * 2 + 1]);
+    const size_t oi = other_per_poly ? (size_t)f * 2 : 0;
+    const int st = div_polynomial_dev<T>(self, len, cmk<T>(other[oi], other[oi + 1]), rem);
+    if (status_out) status_out[f] = (uint8_t)st;
+    for (int i = 0; i < len; ++i) {
+        coeffs[((size_t)f * len + i) * 2] = self[i].re;
+        coeffs[((size_t)f * len + i) * 2 + 1] = self[i].im;
+        if (rem_out) {
+            rem_out[((size_t)f * len + i) * 2] = rem[i].re;
+            rem_out[((size_t)f * len + i) * 2 + 1] = rem[i].im;
+        }
+    }
+}
+
+// roots (complex, any count) → resonances, to_resonance / find_formants semantics
+template <typename T>
+__global__ void __launch_bounds__(128) roots_to_resonances_kernel(const T* __restrict__ roots, int64_t n_frames, int n_roots,
+                                                                  double fs, int strict_im, void* res_out, int out_f64, int R,
+                                                                  int32_t* nres_out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    double rf[kMaxPolyLen], rb[kMaxPolyLen];
+    int cnt = 0;
+    for (int k = 0; k < n_roots; ++k) {
+        double fr_, bw_;
+        if (from_root_f64((double)roots[((size_t)f * n_roots + k) * 2], (double)roots[((size_t)f * n_roots + k) * 2 + 1], fs,
+                          strict_im != 0, &fr_, &bw_)) {
+            rf[cnt] = fr_; rb[cnt] = bw_; ++cnt;
+        }
+    }
+    // stable insertion sort ascending by frequency
+    for (int i = 1; i < cnt; ++i) {
+        const double kf = rf[i], kb = rb[i];
+        int j = i - 1;
+        while (j >= 0 && rf[j] > kf) { rf[j + 1] = rf[j]; rb[j + 1] = rb[j]; --j; }
+        rf[j + 1] = kf; rb[j + 1] = kb;
+    }
+    for (int s = 0; s < R; ++s) {
+        const double a = s < cnt ? rf[s] : 0.0, b = s < cnt ? rb[s] : 0.0;
+        if (out_f64) { reinterpret_cast<double*>(res_out)[((size_t)f * R + s) * 2] = a; reinterpret_cast<double*>(res_out)[((size_t)f * R + s) * 2 + 1] = b; }
+        else { reinterpret_cast<float*>(res_out)[((size_t)f * R + s) * 2] = (float)a; reinterpret_cast<float*>(res_out)[((size_t)f * R + s) * 2 + 1] = (float)b; }
+    }
+    if (nres_out) nres_out[f] = cnt;
+}
+
+// =============================================================================================
+// McCandless tracker
+// =============================================================================================
+struct TrackParams {
+    const void* res;        // [F][R] resonance pairs
+    const int32_t* nres;    // unused by the step (zeros take part), kept for debugging
+    const uint8_t* status;  // per-frame status (frames with an error leave the estimates untouched) or null
+    void* est_inout;        // [n_segments][n_est]
+    void* tracks_out;       // [F][n_est] or null
+    int64_t n_segments, seg_frames;
+    int R, n_res_eff;       // stored slots per frame; number of resonances the step sees (zero padded up to it)
+    int n_est, res_f64, out_f64;
+};
+
+// One warp per utterance (segment).  Lane j holds resonance j of the current frame (32 lanes = the 32
+// zero-padded slots find_formants passes, lib.rs:114); the nearest-peak search of step 2 is a warp
+// arg-min; the <= 6 formant slots and estimates live in registers, identically in every lane, so the
+// sequential steps 3-5 run without divergence; the next frame's resonances are prefetched while the
+// current step runs.  Step 4 only ever touches slots for resonance indices j < 6 (all three of its
+// conditions need j or j±1 to be a slot index), so it is unrolled over j = 0..5.
+__device__ __forceinline__ double ld_pair(const void* p, int f64, size_t idx) {
+    return f64 ? reinterpret_cast<const double*>(p)[idx] : (double)reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st_pair(void* p, int f64, size_t idx, double v) {
+    if (f64) reinterpret_cast<double*>(p)[idx] = v;
+    else reinterpret_cast<float*>(p)[idx] = (float)v;
+}
+
+__global__ void __launch_bounds__(128) tracker_kernel(const TrackParams T) {
+    constexpr int NS = VBX_MAX_FORMANT_SLOTS;
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= T.n_segments) return;
+    const int n_est = T.n_est, n6 = n_est < NS ? n_est : NS;
+    const unsigned FULL = 0xffffffffu;
+    double ef[NS], eb[NS];  // estimates 0..5 (uniform across lanes)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        ef[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2) : 0.0;
+        eb[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2 + 1) : 0.0;
+    }
+    // estimates beyond the 6 slots never change (the zip at spectrum.rs:235 stops at 6 slots)
+    double xf = 0.0, xb = 0.0;
+    if (lane >= NS && lane < n_est) {
+        xf = ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2);
+        xb = ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2 + 1);
+    }
+    const int64_t f0 = u * T.seg_frames;
+    auto load_res = [&](int64_t f, double& rf, double& rb, int& st) {
+        rf = 0.0; rb = 0.0;
+        if (lane < T.R && lane < T.n_res_eff) {
+            rf = ld_pair(T.res, T.res_f64, ((size_t)f * T.R + lane) * 2);
+            rb = ld_pair(T.res, T.res_f64, ((size_t)f * T.R + lane) * 2 + 1);
+        }
+        st = T.status ? (int)T.status[f] : 0;
+    };
+    double nrf, nrb;
+    int nst;
+    load_res(f0, nrf, nrb, nst);
+    for (int64_t j = 0; j < T.seg_frames; ++j) {
+        const int64_t f = f0 + j;
+        const double rf = nrf, rb = nrb;
+        const int st = nst;
+        if (j + 1 < T.seg_frames) load_res(f + 1, nrf, nrb, nst);  // prefetch
+        if (st == VBX_OK) {
+            double sf[NS], sb[NS];
+            bool some[NS];
+            // step 2: nearest resonance per estimate, first wins ties
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                some[k] = false; sf[k] = 0.0; sb[k] = 0.0;
+                if (k < n6) {
+                    double d = (lane < T.n_res_eff) ? fabs(rf - ef[k]) : INFINITY;
+                    // the reference's fold starts from res[0] and replaces only on `<`: a NaN distance never wins
+                    if (d != d) d = INFINITY;
+                    double dmin = d;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, off));
+                    // first (lowest index) resonance at the minimum distance
+                    const int idx = __ffs(__ballot_sync(FULL, d == dmin)) - 1;
+                    sf[k] = __shfl_sync(FULL, rf, idx);
+                    sb[k] = __shfl_sync(FULL, rb, idx);
+                    some[k] = true;
+                }
+            }
+            // step 3: remove duplicates (w = last kept slot)
+            int w = 0;
+            bool has_unassigned = false;
+#pragma unroll
+            for (int r = 1; r < NS; ++r) {
+                if (some[r]) {
+                    double wf = 0.0, wb = 0.0, we = 0.0;
+                    bool wsome = false;
+#pragma unroll
+                    for (int q = 0; q < NS; ++q)
+                        if (q == w) { wf = sf[q]; wb = sb[q]; we = ef[q]; wsome = some[q]; }
+                    if (wsome && sf[r] == wf && sb[r] == wb) {
+                        has_unassigned = true;
+                        if (fabs(sf[r] - ef[r]) < fabs(sf[r] - we)) {
+#pragma unroll
+                            for (int q = 0; q < NS; ++q)
+                                if (q == w) some[q] = false;
+                            w = r;
+                        } else {
+                            some[r] = false;
+                        }
+                    } else {
+                        w = r;
+                    }
+                }
+            }
+            // step 4: unassigned peaks; the resonance index j doubles as the slot index (j < 6 only)
+            if (has_unassigned) {
+#pragma unroll
+                for (int jj = 0; jj < NS; ++jj) {
+                    if (jj < T.n_res_eff) {
+                        const double pf = __shfl_sync(FULL, rf, jj), pb = __shfl_sync(FULL, rb, jj);
+                        bool contained = false;
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) contained = contained || (some[q] && sf[q] == pf && sb[q] == pb);
+                        if (!contained) {
+                            if (!some[jj]) {
+                                some[jj] = true; sf[jj] = pf; sb[jj] = pb;
+                            } else if (jj > 0 && !some[jj > 0 ? jj - 1 : 0]) {
+                                // swap(j, j−1); slots[j] = peak
+                                some[jj - 1 >= 0 ? jj - 1 : 0] = true; sf[jj - 1 >= 0 ? jj - 1 : 0] = sf[jj]; sb[jj - 1 >= 0 ? jj - 1 : 0] = sb[jj];
+                                sf[jj] = pf; sb[jj] = pb;
+                            } else if (jj + 1 < NS && !some[jj + 1 < NS ? jj + 1 : NS - 1]) {
+                                some[jj + 1 < NS ? jj + 1 : NS - 1] = true; sf[jj + 1 < NS ? jj + 1 : NS - 1] = sf[jj]; sb[jj + 1 < NS ? jj + 1 : NS - 1] = sb[jj];
+                                sf[jj] = pf; sb[jj] = pb;
+                            }
+                        }
+                    }
+                }
+            }
+            // step 5: stable sort, None first then ascending frequency (adjacent swaps on strict <)
+#pragma unroll
+            for (int pass = 0; pass < NS - 1; ++pass) {
+#pragma unroll
+                for (int q = 0; q < NS - 1 - pass; ++q) {
+                    // is slot[q+1] < slot[q] ?
+                    bool less;
+                    if (!some[q + 1]) less = some[q];
+                    else if (!some[q]) less = false;
+                    else less = sf[q + 1] < sf[q];
+                    if (less) {
+                        const double tf = sf[q], tb = sb[q]; const bool ts = some[q];
+                        sf[q] = sf[q + 1]; sb[q] = sb[q + 1]; some[q] = some[q + 1];
+                        sf[q + 1] = tf; sb[q + 1] = tb; some[q + 1] = ts;
+                    }
+                }
+            }
+            // winners (Some, f > 0) overwrite the leading estimates
+            int k = 0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                if (some[q] && sf[q] > 0.0 && k < n_est) {
+#pragma unroll
+                    for (int t = 0; t < NS; ++t)
+                        if (t == k) { ef[t] = sf[q]; eb[t] = sb[q]; }
+                    ++k;
+                }
+            }
+        }
+        if (T.tracks_out && lane < n_est) {
+            double of = xf, ob = xb;
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+                if (t == lane) { of = ef[t]; ob = eb[t]; }
+            st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + lane) * 2, of);
+            st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + lane) * 2 + 1, ob);
+        }
+    }
+    if (lane < n6) {
+        double of = 0.0, ob = 0.0;
+#pragma unroll
+        for (int t = 0; t < NS; ++t)
+            if (t == lane) { of = ef[t]; ob = eb[t]; }
+        st_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2, of);
+        st_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2 + 1, ob);
+    }
+}
+
+int root_precision_default() {
+    const char* e = getenv("VBX_ROOTS_F64");
+    return (e && e[0] == '1') ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t vbx_find_formants_real_work_size(int64_t buf_len, int64_t n_coeffs) { return buf_len * 2 + n_coeffs * 23 + 2; }  // lib.rs:30-32
+int64_t vbx_find_formants_complex_work_size(int64_t n_coeffs) { return n_coeffs * 7 + 4; }                                   // lib.rs:34-36
+int64_t vbx_find_roots_work_size(int64_t len) { return len * 6 + 4; }                                                          // polynomial.rs:75-77
+
+int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs_out, uint8_t* status_out, int32_t out_dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, frames);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, p >= 1 && p <= 32, "Burg order must be in 1..32");
+    VBX_REQUIRE(ctx, frames->frame_len >= 2, "frame_len must be >= 2 (b2[len-2] is indexed)");
+    VBX_REQUIRE(ctx, p < frames->frame_len, "Burg order must be < frame_len (`self.len() - i` underflows)");
+    if (frames->n_frames == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, coeffs_out != nullptr, "coeffs_out is NULL");
+    cudaSetDevice(ctx->device);
+    if (frames->dtype == VBX_I16) return launch_burg<int16_t>(ctx, frames, p, coeffs_out, status_out, out_dtype);
+    return launch_burg<float>(ctx, frames, p, coeffs_out, status_out, out_dtype);
+}
+
+int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
+                          int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im, const uint8_t* status_in,
+                          void* res_out, int32_t res_slots, int32_t* nres_out, void* roots_out, uint8_t* status_out,
+                          int32_t out_dtype, int32_t precision) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, lpc_dtype == VBX_F32 || lpc_dtype == VBX_F64, "lpc_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_frames >= 0, "n_frames < 0");
+    VBX_REQUIRE(ctx, lpc_stride >= p + (lpc_has_leading_one ? 1 : 0), "lpc_stride too small for the order");
+    VBX_REQUIRE(ctx, !res_out || res_slots >= 1, "res_slots must be >= 1");
+    VBX_REQUIRE(ctx, precision >= -1 && precision <= 1, "precision must be -1 (default), 0 (f32 + f64 polish) or 1 (f64)");
+    if (n_frames == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, lpc != nullptr, "lpc is NULL");
+    cudaSetDevice(ctx->device);
+    RootsParams Q;
+    Q.lpc = lpc; Q.status_in = status_in; Q.res_out = res_out; Q.nres_out = nres_out; Q.roots_out = roots_out;
+    Q.status_out = status_out; Q.n_frames = n_frames; Q.fs = sample_rate; Q.lpc_stride = lpc_stride;
+    Q.lpc_has_one = lpc_has_leading_one ? 1 : 0; Q.lpc_f64 = (lpc_dtype == VBX_F64); Q.out_f64 = (out_dtype == VBX_F64);
+    Q.R = res_slots; Q.strict_im = strict_im ? 1 : 0; Q.polish_steps = 2;
+    return launch_lpc_roots(ctx, Q, p, precision < 0 ? root_precision_default() : precision);
+}
+
+int vbx_find_roots(vbx_ctx* ctx, const void* coeffs, int32_t dtype, int64_t n_polys, int32_t len, void* roots_out,
+                   uint8_t* status_out) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, len >= 1 && len <= kMaxPolyLen, "polynomial length must be in 1..%d", kMaxPolyLen);
+    VBX_REQUIRE(ctx, n_polys >= 0, "n_polys < 0");
+    if (n_polys == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, coeffs && roots_out, "coeffs / roots_out is NULL");
+    cudaSetDevice(ctx->device);
+    const int64_t grid = (n_polys + 63) / 64;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many polynomials for one launch");
+    if (dtype == VBX_F64)
+        find_roots_generic_kernel<double><<<(unsigned)grid, 64, 0, ctx->stream>>>((const double*)coeffs, n_polys, len, (double*)roots_out, status_out);
+    else
+        find_roots_generic_kernel<float><<<(unsigned)grid, 64, 0, ctx->stream>>>((const float*)coeffs, n_polys, len, (float*)roots_out, status_out);
+    VBX_CHECK_LAUNCH(ctx, "find_roots_generic_kernel");
+    return VBX_OK;
+}
+
+int vbx_laguerre(vbx_ctx* ctx, const void* coeffs, int32_t dtype, int64_t n_polys, int32_t len, double start_re,
+                 double start_im, void* z_out) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, len >= 1 && len <= kMaxPolyLen, "polynomial length must be in 1..%d", kMaxPolyLen);
+    VBX_REQUIRE(ctx, n_polys >= 0, "n_polys < 0");
+    if (n_polys == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, coeffs && z_out, "coeffs / z_out is NULL");
+    cudaSetDevice(ctx->device);
+    const int64_t grid = (n_polys + 63) / 64;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many polynomials for one launch");
+    if (dtype == VBX_F64)
+        laguerre_generic_kernel<double><<<(unsigned)grid, 64, 0, ctx->stream>>>((const double*)coeffs, n_polys, len, start_re, start_im, (double*)z_out);
+    else
+        laguerre_generic_kernel<float><<<(unsigned)grid, 64, 0, ctx->stream>>>((const float*)coeffs, n_polys, len, (float)start_re, (float)start_im, (float*)z_out);
+    VBX_CHECK_LAUNCH(ctx, "laguerre_generic_kernel");
+    return VBX_OK;
+}
+
+int vbx_div_polynomial(vbx_ctx* ctx, void* coeffs_inout, int32_t dtype, int64_t n_polys, int32_t len, const void* other,
+                       int32_t other_per_poly, void* rem_out, uint8_t* status_out) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, len >= 1 && len <= kMaxPolyLen, "polynomial length must be in 1..%d", kMaxPolyLen);
+    VBX_REQUIRE(ctx, n_polys >= 0, "n_polys < 0");
+    if (n_polys == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, coeffs_inout && other, "coeffs / other is NULL");
+    cudaSetDevice(ctx->device);
+    const int64_t grid = (n_polys + 63) / 64;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many polynomials for one launch");
+    if (dtype == VBX_F64)
+        div_polynomial_generic_kernel<double><<<(unsigned)grid, 64, 0, ctx->stream>>>((double*)coeffs_inout, n_polys, len, (const double*)other, other_per_poly, (double*)rem_out, status_out);
+    else
+        div_polynomial_generic_kernel<float><<<(unsigned)grid, 64, 0, ctx->stream>>>((float*)coeffs_inout, n_polys, len, (const float*)other, other_per_poly, (float*)rem_out, status_out);
+    VBX_CHECK_LAUNCH(ctx, "div_polynomial_generic_kernel");
+    return VBX_OK;
+}
+
+int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dtype, int64_t n_frames, int32_t n_roots,
+                            double sample_rate, int32_t strict_im, void* res_out, int32_t res_slots, int32_t* nres_out,
+                            int32_t out_dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_roots >= 0 && n_roots <= kMaxPolyLen, "n_roots must be in 0..%d", kMaxPolyLen);
+    VBX_REQUIRE(ctx, res_slots >= 1 && n_frames >= 0, "res_slots must be >= 1");
+    if (n_frames == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, (roots || n_roots == 0) && res_out, "roots / res_out is NULL");
+    cudaSetDevice(ctx->device);
+    const int64_t grid = (n_frames + 127) / 128;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+    if (dtype == VBX_F64)
+        roots_to_resonances_kernel<double><<<(unsigned)grid, 128, 0, ctx->stream>>>((const double*)roots, n_frames, n_roots, sample_rate, strict_im, res_out, out_dtype == VBX_F64, res_slots, nres_out);
+    else
+        roots_to_resonances_kernel<float><<<(unsigned)grid, 128, 0, ctx->stream>>>((const float*)roots, n_frames, n_roots, sample_rate, strict_im, res_out, out_dtype == VBX_F64, res_slots, nres_out);
+    VBX_CHECK_LAUNCH(ctx, "roots_to_resonances_kernel");
+    return VBX_OK;
+}
+
+int vbx_estimate_formants(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
+                          int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
+                          int32_t n_estimates, void* tracks_out, int32_t dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, res_dtype == VBX_F32 || res_dtype == VBX_F64, "res_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, res_slots >= 1, "res_slots must be >= 1");
+    VBX_REQUIRE(ctx, n_resonances >= 1 && n_resonances <= VBX_MAX_RESONANCES, "n_resonances must be in 1..%d (resonances[0] is indexed)", VBX_MAX_RESONANCES);
+    VBX_REQUIRE(ctx, n_estimates >= 0 && n_estimates <= VBX_MAX_RESONANCES, "n_estimates must be in 0..%d", VBX_MAX_RESONANCES);
+    VBX_REQUIRE(ctx, n_segments >= 0 && frames_per_segment >= 0, "negative counts");
+    if (n_segments == 0 || frames_per_segment == 0 || n_estimates == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, resonances && est_inout, "resonances / est_inout is NULL");
+    cudaSetDevice(ctx->device);
+    TrackParams T;
+    T.res = resonances; T.nres = nullptr; T.status = status_in; T.est_inout = est_inout; T.tracks_out = tracks_out;
+    T.n_segments = n_segments; T.seg_frames = frames_per_segment; T.R = res_slots; T.n_res_eff = n_resonances;
+    T.n_est = n_estimates; T.res_f64 = (res_dtype == VBX_F64); T.out_f64 = (dtype == VBX_F64);
+    const int64_t grid = (n_segments + 3) / 4;  // one warp per segment
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
+    tracker_kernel<<<(unsigned)grid, 128, 0, ctx->stream>>>(T);
+    VBX_CHECK_LAUNCH(ctx, "tracker_kernel");
+    return VBX_OK;
+}
+
+// lib.rs:40-116 find_formants, batched: LPC (Burg on the frame as windowed by frames->window — HANN_PERIODIC
+// for the reference's own in-line window — or autocorrelation + Levinson) → roots → resonances (im > 0,
+// sorted, zero padded to 32) → McCandless step per frame, sequential inside each segment (utterance).
+int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs, int32_t lpc_method,
+                      void* est_inout, int32_t n_formants, void* tracks_out, void* resonances_out, int32_t* nres_out,
+                      uint8_t* status_out, int32_t dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, frames);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, lpc_method == VBX_LPC_BURG || lpc_method == VBX_LPC_AUTOCORR, "unknown lpc_method");
+    VBX_REQUIRE(ctx, n_coeffs >= 2 && n_coeffs <= kMaxRootsOrder, "n_coeffs must be in 2..%d", kMaxRootsOrder);
+    VBX_REQUIRE(ctx, n_coeffs < frames->frame_len, "n_coeffs must be < frame_len");
+    VBX_REQUIRE(ctx, n_formants >= 0 && n_formants <= VBX_MAX_RESONANCES, "n_formants must be in 0..%d", VBX_MAX_RESONANCES);
+    const int64_t F = frames->n_frames;
+    if (F == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    const int p = n_coeffs;
+    // scratch: lpc [F][p+1] f64 | status [F] | resonances [F][p] pairs (if the caller does not want them)
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t lpc_bytes = al((size_t)F * (p + 1) * sizeof(double));
+    const size_t st_bytes = al((size_t)F);
+    const size_t res_es = (dtype == VBX_F64) ? 16 : 8;
+    const bool own_res = (resonances_out == nullptr);
+    const int R = own_res ? p : VBX_MAX_RESONANCES;
+    const size_t res_bytes = own_res ? al((size_t)F * R * res_es) : 0;
+    st = vbx_arena_reserve(ctx, lpc_bytes + 2 * st_bytes + res_bytes);
+    if (st != VBX_OK) return st;
+    char* base = (char*)ctx->arena;
+    double* d_lpc = (double*)base;
+    uint8_t* d_st_lpc = (uint8_t*)(base + lpc_bytes);
+    uint8_t* d_st = status_out ? status_out : (uint8_t*)(base + lpc_bytes + st_bytes);
+    void* d_res = own_res ? (void*)(base + lpc_bytes + 2 * st_bytes) : resonances_out;
+    const uint8_t* lpc_status = nullptr;
+    int lpc_stride, has_one;
+    if (lpc_method == VBX_LPC_BURG) {
+        st = vbx_lpc_burg(ctx, frames, p, d_lpc, d_st_lpc, VBX_F64);
+        lpc_status = d_st_lpc;
+        lpc_stride = p;
+        has_one = 0;
+    } else {
+        st = vbx_lpc(ctx, frames, p, nullptr, d_lpc, nullptr, VBX_F64);
+        lpc_stride = p + 1;
+        has_one = 1;
+    }
+    if (st != VBX_OK) return st;
+    st = vbx_lpc_to_resonances(ctx, d_lpc, VBX_F64, F, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
+                               d_res, R, nres_out, nullptr, d_st, dtype, -1);
+    if (st != VBX_OK) return st;
+    if (n_formants > 0 && est_inout) {
+        const int64_t J = vbx_frames_per_segment(frames);
+        st = vbx_estimate_formants(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, F / J, J, d_st, est_inout, n_formants, tracks_out, dtype);
+        if (st != VBX_OK) return st;
+    }
+    return VBX_OK;
+}
+
+}  // extern "C"
+
+// host twin of vbx_find_formants: H2D the audio extent + starting estimates, run, D2H everything requested
+extern "C" int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
+                                      int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
+                                      void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, frames);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    const int64_t F = frames->n_frames;
+    if (F == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    const size_t pair = (dtype == VBX_F64) ? 16 : 8;
+    const int64_t J = vbx_frames_per_segment(frames), segs = F / J;
+    const size_t in_bytes = (size_t)vbx_frames_extent(frames) * vbx_dtype_size(frames->dtype);
+    const size_t est_bytes = (est_inout && n_formants > 0) ? (size_t)segs * n_formants * pair : 0;
+    const size_t trk_bytes = (tracks_out && n_formants > 0) ? (size_t)F * n_formants * pair : 0;
+    const size_t res_bytes = resonances_out ? (size_t)F * VBX_MAX_RESONANCES * pair : 0;
+    const size_t nres_bytes = nres_out ? (size_t)F * 4 : 0;
+    const size_t st_bytes = status_out ? (size_t)F : 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // a private device block (the pipeline itself uses the context arena)
+    void* blk = nullptr;
+    const size_t total = al(in_bytes) + al(est_bytes) + al(trk_bytes) + al(res_bytes) + al(nres_bytes) + al(st_bytes);
+    cudaError_t e = cudaMalloc(&blk, total);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return vbx_fail(ctx, VBX_ERR_NOMEM, "find_formants_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+    }
+    char* p = (char*)blk;
+    void* d_in = p; p += al(in_bytes);
+    void* d_est = est_bytes ? p : nullptr; p += al(est_bytes);
+    void* d_trk = trk_bytes ? p : nullptr; p += al(trk_bytes);
+    void* d_res = res_bytes ? p : nullptr; p += al(res_bytes);
+    int32_t* d_nres = nres_bytes ? (int32_t*)p : nullptr; p += al(nres_bytes);
+    uint8_t* d_st = st_bytes ? (uint8_t*)p : nullptr;
+    auto run = [&]() -> int {
+        VBX_CUDA(ctx, cudaMemcpyAsync(d_in, frames->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (est_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(d_est, est_inout, est_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        vbx_frames dfr = *frames;
+        dfr.base = d_in;
+        int s = vbx_find_formants(ctx, &dfr, sample_rate, n_coeffs, lpc_method, d_est, n_formants, d_trk, d_res, d_nres, d_st, dtype);
+        if (s != VBX_OK) return s;
+        if (est_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(est_inout, d_est, est_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (trk_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(tracks_out, d_trk, trk_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(resonances_out, d_res, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nres_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(nres_out, d_nres, nres_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (st_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(status_out, d_st, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return VBX_OK;
+    };
+    st = run();
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(blk);
+    return st;
+}

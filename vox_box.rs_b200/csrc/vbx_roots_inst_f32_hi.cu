@@ -1,0 +1,5 @@
+// instantiates lpc_roots_kernel<P, float> for P = 13..24 (see vbx_roots_kernel.cuh)
+#include "vbx_roots_kernel.cuh"
+namespace vbx_roots {
+void fill_f32_hi(roots_kernel_t* t) { RootsFill<float, 13, 24>::fill(t); }
+}  // namespace vbx_roots

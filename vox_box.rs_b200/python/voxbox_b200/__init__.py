@@ -20,6 +20,7 @@ OK, ERR_LPC, ERR_PITCH, ERR_POLYNOMIAL, ERR_WORKSPACE, ERR_CUDA, ERR_BADARG, ERR
 F32, F64, I16 = 0, 1, 2
 WINDOW_NONE, WINDOW_HANN_SYMMETRIC, WINDOW_HANN_PERIODIC = 0, 1, 2
 MAX_RESONANCES = 32
+LPC_BURG, LPC_AUTOCORR = 0, 1
 _NP = {F32: np.float32, F64: np.float64, I16: np.int16}
 
 
@@ -87,6 +88,19 @@ def _declare(L):
     sig("vbx_lpc_levinson", C.c_int, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32)
     sig("vbx_lpc", C.c_int, _vp, _frp, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_lpc_host", C.c_int, _vp, _frp, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_lpc_burg", C.c_int, _vp, _frp, _i32, _vp, _vp, _i32)
+    sig("vbx_find_roots", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp, _vp)
+    sig("vbx_find_roots_work_size", _i64, _i64)
+    sig("vbx_laguerre", C.c_int, _vp, _vp, _i32, _i64, _i32, C.c_double, C.c_double, _vp)
+    sig("vbx_div_polynomial", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp)
+    sig("vbx_roots_to_resonances", C.c_int, _vp, _vp, _i32, _i64, _i32, C.c_double, _i32, _vp, _i32, _vp, _i32)
+    sig("vbx_lpc_to_resonances", C.c_int, _vp, _vp, _i32, _i64, _i32, _i32, _i32, C.c_double, _i32, _vp, _vp, _i32, _vp,
+        _vp, _vp, _i32, _i32)
+    sig("vbx_estimate_formants", C.c_int, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _i32)
+    sig("vbx_find_formants_real_work_size", _i64, _i64, _i64)
+    sig("vbx_find_formants_complex_work_size", _i64, _i64)
+    sig("vbx_find_formants", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
+    sig("vbx_find_formants_host", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
 
 
 def window_table(window, n):
@@ -250,3 +264,141 @@ class Context:
                                           ac.ctypes.data if ac is not None else None,
                                           kc.ctypes.data if kc is not None else None, out_dtype), "vbx_lpc_host")
         return r, ac, kc
+
+
+# ---- formant path (appended to Context) ---------------------------------------------------------
+def _dt_of(a):
+    return F64 if np.dtype(a.dtype) in (np.dtype(np.float64), np.dtype(np.complex128)) else F32
+
+
+def _lpc_burg(self, frames, p, out_dtype=F64):
+    """spectrum.rs:94-146 lpc_praat over frames → (coeffs [F][p], status [F]) device arrays."""
+    co = self.empty((frames.n_frames, p), _NP[out_dtype])
+    st = self.empty((frames.n_frames,), np.uint8)
+    self._check(self.lib.vbx_lpc_burg(self.h, C.byref(frames), p, co.ptr, st.ptr, out_dtype), "vbx_lpc_burg")
+    return co, st
+
+
+def _find_roots(self, coeffs):
+    """polynomial.rs:92-152 find_roots_mut on host complex arrays [F][len] → (buffer after write-back, status)."""
+    c = np.ascontiguousarray(coeffs)
+    assert c.dtype in (np.complex64, np.complex128) and c.ndim == 2
+    d = self.to_device(c)
+    out = self.empty(c.shape, c.dtype)
+    st = self.empty((c.shape[0],), np.uint8)
+    self._check(self.lib.vbx_find_roots(self.h, d.ptr, _dt_of(c), c.shape[0], c.shape[1], out.ptr, st.ptr), "vbx_find_roots")
+    return out.to_host(), st.to_host()
+
+
+def _laguerre(self, coeffs, start):
+    c = np.ascontiguousarray(coeffs)
+    assert c.dtype in (np.complex64, np.complex128) and c.ndim == 2
+    d = self.to_device(c)
+    z = self.empty((c.shape[0],), c.dtype)
+    self._check(self.lib.vbx_laguerre(self.h, d.ptr, _dt_of(c), c.shape[0], c.shape[1], start.real, start.imag, z.ptr),
+                "vbx_laguerre")
+    return z.to_host()
+
+
+def _div_polynomial(self, coeffs, other):
+    c = np.ascontiguousarray(coeffs)
+    assert c.dtype in (np.complex64, np.complex128) and c.ndim == 2
+    d = self.to_device(c)
+    o = self.to_device(np.asarray([other], dtype=c.dtype))
+    rem = self.empty(c.shape, c.dtype)
+    st = self.empty((c.shape[0],), np.uint8)
+    self._check(self.lib.vbx_div_polynomial(self.h, d.ptr, _dt_of(c), c.shape[0], c.shape[1], o.ptr, 0, rem.ptr, st.ptr),
+                "vbx_div_polynomial")
+    return d.to_host(), rem.to_host(), st.to_host()
+
+
+def _roots_to_resonances(self, roots, fs, strict_im=False, res_slots=None, out_dtype=F64):
+    r = np.ascontiguousarray(roots)
+    assert r.dtype in (np.complex64, np.complex128) and r.ndim == 2
+    slots = res_slots or max(r.shape[1], 1)
+    d = self.to_device(r)
+    res = self.empty((r.shape[0], slots, 2), _NP[out_dtype])
+    n = self.empty((r.shape[0],), np.int32)
+    self._check(self.lib.vbx_roots_to_resonances(self.h, d.ptr, _dt_of(r), r.shape[0], r.shape[1], fs, int(strict_im),
+                                                 res.ptr, slots, n.ptr, out_dtype), "vbx_roots_to_resonances")
+    return res.to_host(), n.to_host()
+
+
+def _lpc_to_resonances(self, lpc, p, has_one, fs, strict_im=True, res_slots=None, out_dtype=F64, precision=-1,
+                       status_in=None, want_roots=False):
+    """lpc: DeviceArray [F][stride].  Returns dict of device arrays."""
+    F, stride = lpc.shape
+    slots = res_slots or p
+    res = self.empty((F, slots, 2), _NP[out_dtype])
+    n = self.empty((F,), np.int32)
+    st = self.empty((F,), np.uint8)
+    roots = self.empty((F, p, 2), _NP[out_dtype]) if want_roots else None
+    self._check(self.lib.vbx_lpc_to_resonances(self.h, lpc.ptr, _dt_of(lpc), F, stride, p, int(has_one), fs, int(strict_im),
+                                               status_in.ptr if status_in is not None else None, res.ptr, slots, n.ptr,
+                                               roots.ptr if roots else None, st.ptr, out_dtype, precision),
+                "vbx_lpc_to_resonances")
+    return dict(resonances=res, n_res=n, status=st, roots=roots)
+
+
+def _estimate_formants(self, resonances, estimates, n_segments=1, n_resonances=None, dtype=F64):
+    """FormantExtractor over host arrays: resonances [F][slots][2], estimates [n_segments][k][2] (or [k][2]).
+    Returns (tracks [F][k][2], final estimates)."""
+    res = np.ascontiguousarray(resonances, dtype=_NP[dtype])
+    est = np.ascontiguousarray(estimates, dtype=_NP[dtype]).reshape(n_segments, -1, 2)
+    F, slots = res.shape[0], res.shape[1]
+    k = est.shape[1]
+    d_res, d_est = self.to_device(res), self.to_device(est)
+    tracks = self.empty((F, k, 2), _NP[dtype])
+    self._check(self.lib.vbx_estimate_formants(self.h, d_res.ptr, dtype, slots, n_resonances or slots, n_segments,
+                                               F // n_segments, None, d_est.ptr, k, tracks.ptr, dtype),
+                "vbx_estimate_formants")
+    return tracks.to_host(), d_est.to_host()
+
+
+def _find_formants(self, frames, fs, p, method, estimates, dtype=F64, want_resonances=True):
+    """Device-pointer find_formants.  estimates: host [n_segments][k][2].  Returns dict of host arrays."""
+    F = frames.n_frames
+    J = frames.frames_per_segment or F
+    segs = F // J if J else 0
+    est = np.ascontiguousarray(estimates, dtype=_NP[dtype])
+    k = est.shape[-2]
+    est = est.reshape(segs, k, 2)
+    d_est = self.to_device(est)
+    tracks = self.empty((F, k, 2), _NP[dtype])
+    res = self.empty((F, MAX_RESONANCES, 2), _NP[dtype]) if want_resonances else None
+    nres = self.empty((F,), np.int32)
+    st = self.empty((F,), np.uint8)
+    self._check(self.lib.vbx_find_formants(self.h, C.byref(frames), fs, p, method, d_est.ptr, k, tracks.ptr,
+                                           res.ptr if res else None, nres.ptr, st.ptr, dtype), "vbx_find_formants")
+    return dict(tracks=tracks.to_host(), estimates=d_est.to_host(), resonances=res.to_host() if res else None,
+                n_res=nres.to_host(), status=st.to_host())
+
+
+def _find_formants_host(self, audio, n_frames, frame_len, stride, window, fs, p, method, estimates, dtype=F64,
+                        frames_per_segment=0, segment_stride=0):
+    audio = np.ascontiguousarray(audio)
+    fr = self.frames(audio.ctypes.data, n_frames, frame_len, stride, window, I16 if audio.dtype == np.int16 else F32,
+                     frames_per_segment, segment_stride)
+    J = frames_per_segment or n_frames
+    segs = n_frames // J if J else 0
+    est = np.ascontiguousarray(estimates, dtype=_NP[dtype]).reshape(segs, -1, 2).copy()
+    k = est.shape[1]
+    tracks = np.zeros((n_frames, k, 2), dtype=_NP[dtype])
+    res = np.zeros((n_frames, MAX_RESONANCES, 2), dtype=_NP[dtype])
+    nres = np.zeros(n_frames, dtype=np.int32)
+    st = np.zeros(n_frames, dtype=np.uint8)
+    self._check(self.lib.vbx_find_formants_host(self.h, C.byref(fr), fs, p, method, est.ctypes.data, k, tracks.ctypes.data,
+                                                res.ctypes.data, nres.ctypes.data, st.ctypes.data, dtype),
+                "vbx_find_formants_host")
+    return dict(tracks=tracks, estimates=est, resonances=res, n_res=nres, status=st)
+
+
+Context.lpc_burg = _lpc_burg
+Context.find_roots = _find_roots
+Context.laguerre = _laguerre
+Context.div_polynomial = _div_polynomial
+Context.roots_to_resonances = _roots_to_resonances
+Context.lpc_to_resonances = _lpc_to_resonances
+Context.estimate_formants = _estimate_formants
+Context.find_formants = _find_formants
+Context.find_formants_host = _find_formants_host
