@@ -59,7 +59,14 @@ typedef enum vbx_dtype { VBX_F32 = 0, VBX_F64 = 1, VBX_I16 = 2 } vbx_dtype;
  *                   periodic.rs:493): 0.5(1-cos 2πφ), φ accumulated in steps of 1/(N-1);
  *  HANN_PERIODIC  = the in-line window of find_formants (lib.rs:66-70): φ = i/N;
  *  NONE           = frame is used as is (Windower::rectangle, tests/lib.rs:71). */
-typedef enum vbx_window { VBX_WINDOW_NONE = 0, VBX_WINDOW_HANN_SYMMETRIC = 1, VBX_WINDOW_HANN_PERIODIC = 2 } vbx_window;
+typedef enum vbx_window {
+    VBX_WINDOW_NONE = 0,
+    VBX_WINDOW_HANN_SYMMETRIC = 1,
+    VBX_WINDOW_HANN_PERIODIC = 2,
+    /* periodic.rs:232-252 HanningLag (`LagType for Hanning`): the Hann window's autocorrelation over the same
+     * accumulated phases.  Only valid for vbx_window_table_host (vbx_pitch uses it internally), not as frames.window. */
+    VBX_WINDOW_HANN_LAG = 3
+} vbx_window;
 
 /* A batch of frames as a strided view: frame f = base[f*frame_stride .. f*frame_stride + frame_len).
  * frame_stride == frame_len is a packed [F, N] tensor; frame_stride == hop < frame_len is the
@@ -221,6 +228,35 @@ VBX_API int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sam
 VBX_API int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
                                    int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
                                    void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
+
+/* ---- periodic.rs:356-456  Pitched::pitch::<Hanning> (+ LocalMaxima :362-375, Pitch :306-318) --------------------- */
+/* Boersma autocorrelation pitch candidates for every frame of the view (the frame is windowed by frames->window as
+ * the reference's callers do, Windower::hanning => HANN_SYMMETRIC; the lag window is HanningLag, the only LagType).
+ * The reference ignores its local_peak / global_peak arguments (periodic.rs:396), so they are not parameters.
+ * cand_out: [F][max_candidates] (frequency, strength) pairs of out_dtype, sorted by strength descending exactly as
+ * the returned Vec (stable; the unvoiced candidate {0, threshold} is always part of it), zero padded;
+ * n_cand_out[f] (optional) = length of the reference's Vec (may exceed max_candidates: the list is truncated);
+ * status_out[f] (optional) = VBX_ERR_PITCH where a strength is NaN (the reference panics in its sort) — such frames
+ * return their candidates unsorted.  The lag sweep runs on the FP32 FMA pipe (fp64 partial-sum folding), everything
+ * after it in fp64.  frame_len <= 16384. */
+VBX_API int vbx_pitch(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double threshold, double min_hz,
+                      double max_hz, int32_t max_candidates, void* cand_out, int32_t* n_cand_out, uint8_t* status_out,
+                      int32_t out_dtype);
+VBX_API int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double threshold, double min_hz,
+                           double max_hz, int32_t max_candidates, void* cand_out, int32_t* n_cand_out,
+                           uint8_t* status_out, int32_t out_dtype);
+/* periodic.rs:320-354 PitchExtractor::next: out[f] = candidates[f][0] (arg-max; the cost fields are unused). */
+VBX_API int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_frames, int32_t max_candidates,
+                              void* out);
+/* periodic.rs:29-87 interpolate_sinc(y, offset, nx, x, max_depth), batched: y [n_series][y_len] f64,
+ * x [n_series][n_points] f64 -> out [n_series][n_points].  Indices the reference would panic on give NaN. */
+VBX_API int vbx_interpolate_sinc(vbx_ctx* ctx, const double* y, int64_t n_series, int64_t y_len, int64_t offset,
+                                 int64_t nx, const double* x, int64_t n_points, int64_t max_depth, double* out);
+/* periodic.rs:192-230 improve_extremum (+ brent_maximize :103-188), batched like vbx_interpolate_sinc.
+ * interpolation: 0 = Interpolation::None, 1 = Parabolic, 2 = Sinc(sinc_depth). */
+VBX_API int vbx_improve_extremum(vbx_ctx* ctx, const double* y, int64_t n_series, int64_t y_len, int64_t offset,
+                                 int64_t nx, const double* ixmid, int64_t n_points, int32_t interpolation,
+                                 int64_t sinc_depth, int32_t is_max, double* xmid_out, double* ymid_out);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,8 @@ int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes) {
 //  - HANN_SYMMETRIC: sample::window::Window::<_, Hanning>::new(n): phase starts at 0 and is
 //    ACCUMULATED, phase = (phase + 1/(n-1)) % 1.0, value 0.5·(1 − cos(2π·phase));
 //  - HANN_PERIODIC:  lib.rs:66-70, phase = i · (1/n);
+//  - HANN_LAG: the autocorrelation of the Hann window, HanningLag (periodic.rs:236-247), same phases
+//    as HANN_SYMMETRIC — a table for the pitch path, not a frame window;
 //  - NONE: ones (the multiply by 1.0 is exact).
 void vbx_window_fill_host(int kind, int n, double* out) {
     const double PI = 3.14159265358979323846264338327950288;
@@ -73,6 +75,15 @@ void vbx_window_fill_host(int kind, int n, double* out) {
     } else if (kind == VBX_WINDOW_HANN_PERIODIC) {
         double len_inv = 1.0 / (double)n;
         for (int i = 0; i < n; ++i) out[i] = 0.5 * (1.0 - cos(2.0 * PI * ((double)i * len_inv)));
+    } else if (kind == VBX_WINDOW_HANN_LAG) {
+        // periodic.rs:236-247 HanningLag::at_phase over Window::new(n)'s accumulated phases (periodic.rs:400)
+        double step = 1.0 / ((double)n - 1.0), phase = 0.0;
+        const double pi_2 = PI * 2.0;
+        for (int i = 0; i < n; ++i) {
+            const double v = phase * pi_2;
+            out[i] = (1.0 - phase) * (2.0 / 3.0 + (1.0 / 3.0) * cos(v)) + (1.0 / pi_2) * sin(v);
+            phase = fmod(phase + step, 1.0);
+        }
     } else {
         for (int i = 0; i < n; ++i) out[i] = 1.0;
     }
@@ -299,7 +310,7 @@ int vbx_measure_peaks(vbx_ctx* ctx, double* fp32_tflops, double* fp64_tflops) {
 }
 
 int vbx_window_table_host(int window, int32_t n, double* out) {
-    if (n < 1 || !out || window < VBX_WINDOW_NONE || window > VBX_WINDOW_HANN_PERIODIC) return VBX_ERR_BADARG;
+    if (n < 1 || !out || window < VBX_WINDOW_NONE || window > VBX_WINDOW_HANN_LAG) return VBX_ERR_BADARG;
     vbx_window_fill_host(window, n, out);
     return VBX_OK;
 }

@@ -18,7 +18,8 @@ HEADER_PATH = os.path.join(os.path.dirname(ROOT), "include", "voxbox_b200.h")
 
 OK, ERR_LPC, ERR_PITCH, ERR_POLYNOMIAL, ERR_WORKSPACE, ERR_CUDA, ERR_BADARG, ERR_NOMEM = range(8)
 F32, F64, I16 = 0, 1, 2
-WINDOW_NONE, WINDOW_HANN_SYMMETRIC, WINDOW_HANN_PERIODIC = 0, 1, 2
+WINDOW_NONE, WINDOW_HANN_SYMMETRIC, WINDOW_HANN_PERIODIC, WINDOW_HANN_LAG = 0, 1, 2, 3
+INTERP_NONE, INTERP_PARABOLIC, INTERP_SINC = 0, 1, 2
 MAX_RESONANCES = 32
 LPC_BURG, LPC_AUTOCORR = 0, 1
 _NP = {F32: np.float32, F64: np.float64, I16: np.int16}
@@ -101,6 +102,12 @@ def _declare(L):
     sig("vbx_find_formants_complex_work_size", _i64, _i64)
     sig("vbx_find_formants", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
     sig("vbx_find_formants_host", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
+    _d = C.c_double
+    sig("vbx_pitch", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_pitch_host", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_pitch_extract", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
+    sig("vbx_interpolate_sinc", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp)
+    sig("vbx_improve_extremum", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp)
 
 
 def window_table(window, n):
@@ -402,3 +409,65 @@ Context.lpc_to_resonances = _lpc_to_resonances
 Context.estimate_formants = _estimate_formants
 Context.find_formants = _find_formants
 Context.find_formants_host = _find_formants_host
+
+
+# ---- pitch path (appended to Context) -------------------------------------------------------------
+def _pitch(self, frames, fs, threshold, fmin, fmax, max_cand=16, out_dtype=F64):
+    """periodic.rs:356-456 pitch::<Hanning> over frames → dict of device arrays
+    (candidates [F][max_cand][2] sorted by strength desc, n_cand [F], status [F])."""
+    F = frames.n_frames
+    cand = self.empty((F, max_cand, 2), _NP[out_dtype])
+    n = self.empty((F,), np.int32)
+    st = self.empty((F,), np.uint8)
+    self._check(self.lib.vbx_pitch(self.h, C.byref(frames), fs, threshold, fmin, fmax, max_cand, cand.ptr, n.ptr, st.ptr,
+                                   out_dtype), "vbx_pitch")
+    return dict(candidates=cand, n_cand=n, status=st)
+
+
+def _pitch_host(self, audio, n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, max_cand=16, out_dtype=F64,
+                frames_per_segment=0, segment_stride=0):
+    audio = np.ascontiguousarray(audio)
+    fr = self.frames(audio.ctypes.data, n_frames, frame_len, stride, window, I16 if audio.dtype == np.int16 else F32,
+                     frames_per_segment, segment_stride)
+    cand = np.zeros((n_frames, max_cand, 2), dtype=_NP[out_dtype])
+    n = np.zeros(n_frames, dtype=np.int32)
+    st = np.zeros(n_frames, dtype=np.uint8)
+    self._check(self.lib.vbx_pitch_host(self.h, C.byref(fr), fs, threshold, fmin, fmax, max_cand, cand.ctypes.data,
+                                        n.ctypes.data, st.ctypes.data, out_dtype), "vbx_pitch_host")
+    return dict(candidates=cand, n_cand=n, status=st)
+
+
+def _pitch_extract(self, cand):
+    """periodic.rs:320-354 PitchExtractor: strongest candidate per frame."""
+    F, max_cand = cand.shape[0], cand.shape[1]
+    out = self.empty((F, 2), cand.dtype)
+    self._check(self.lib.vbx_pitch_extract(self.h, cand.ptr, _dt_of(cand), F, max_cand, out.ptr), "vbx_pitch_extract")
+    return out
+
+
+def _interpolate_sinc(self, y, offset, nx, x, max_depth):
+    """periodic.rs:29-87 on host arrays: y [S][y_len] (or [y_len]), x [S][M] (or [M]) → values [S][M]."""
+    y = np.atleast_2d(np.ascontiguousarray(y, dtype=np.float64))
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(y.shape[0], -1)
+    dy, dx = self.to_device(y), self.to_device(x)
+    out = self.empty(x.shape, np.float64)
+    self._check(self.lib.vbx_interpolate_sinc(self.h, dy.ptr, y.shape[0], y.shape[1], offset, nx, dx.ptr, x.shape[1],
+                                              max_depth, out.ptr), "vbx_interpolate_sinc")
+    return out.to_host()
+
+
+def _improve_extremum(self, y, offset, nx, ixmid, interp=INTERP_SINC, depth=1200, is_max=True):
+    y = np.atleast_2d(np.ascontiguousarray(y, dtype=np.float64))
+    x = np.ascontiguousarray(ixmid, dtype=np.float64).reshape(y.shape[0], -1)
+    dy, dx = self.to_device(y), self.to_device(x)
+    xm, ym = self.empty(x.shape, np.float64), self.empty(x.shape, np.float64)
+    self._check(self.lib.vbx_improve_extremum(self.h, dy.ptr, y.shape[0], y.shape[1], offset, nx, dx.ptr, x.shape[1],
+                                              interp, depth, int(is_max), xm.ptr, ym.ptr), "vbx_improve_extremum")
+    return xm.to_host(), ym.to_host()
+
+
+Context.pitch = _pitch
+Context.pitch_host = _pitch_host
+Context.pitch_extract = _pitch_extract
+Context.interpolate_sinc = _interpolate_sinc
+Context.improve_extremum = _improve_extremum
