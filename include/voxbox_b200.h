@@ -258,6 +258,38 @@ VBX_API int vbx_improve_extremum(vbx_ctx* ctx, const double* y, int64_t n_series
                                  int64_t nx, const double* ixmid, int64_t n_points, int32_t interpolation,
                                  int64_t sinc_depth, int32_t is_max, double* xmid_out, double* ymid_out);
 
+/* ---- spectrum.rs:371-441  MFCC::mfcc, hz_to_mel, mel_to_hz, dct, dct_mut ------------------------------------------ */
+/* mfcc(num_coeffs, (freq_lo, freq_hi), sample_rate) on every (windowed) frame.  The reference has ONE parameter
+ * `num_coeffs` that is both the number of mel bands and the number of DCT rows it returns (spectrum.rs:410-414,437-439);
+ * n_keep <= num_coeffs keeps only the first n_keep DCT rows ("13 coefficients from 40 bands" = num_coeffs 40, n_keep 13;
+ * n_keep == num_coeffs is the drop-in).  out: [F][n_keep]; energies_out (optional): [F][num_coeffs] log-energies before
+ * the DCT.  VBX_ERR_BADARG where the reference panics (a filter-bank bin beyond the spectrum / decreasing bins).
+ * The FFT (rustfft's unnormalised forward DFT) runs in fp64 by default — vbx_mfcc_set_fft_precision(ctx, VBX_F32)
+ * selects an fp32 transform (faster, ~1e-6 relative error on the band sums, which can exceed the 1e-5 bound on quiet
+ * frames whose band sums sit near the log10 clamp); band sums, log10 and DCT are always fp64. */
+VBX_API int vbx_mfcc(vbx_ctx* ctx, const vbx_frames* frames, int32_t num_coeffs, int32_t n_keep, double freq_lo,
+                     double freq_hi, double sample_rate, void* out, void* energies_out, int32_t out_dtype);
+VBX_API int vbx_mfcc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t num_coeffs, int32_t n_keep, double freq_lo,
+                          double freq_hi, double sample_rate, void* out, int32_t out_dtype);
+VBX_API int vbx_mfcc_set_fft_precision(vbx_ctx* ctx, int32_t dtype); /* VBX_F64 (default) or VBX_F32 */
+VBX_API double vbx_hz_to_mel(double hz);  /* spectrum.rs:375-377 (host) */
+VBX_API double vbx_mel_to_hz(double mel); /* spectrum.rs:379-381 (host) */
+/* dct / dct_mut (spectrum.rs:384-398): coeffs[s][k] = 2 Σ_m signal[s][m] cos(πk(2m+1)/(2n)), [n_signals][n] of dtype. */
+VBX_API int vbx_dct(vbx_ctx* ctx, const void* signal, int32_t dtype, int64_t n_signals, int32_t n, void* coeffs);
+
+/* ---- waves.rs:10-96  RMS, MaxAmplitude, Normalize, Filter::preemphasis ----------------------------------------------- */
+/* Signals are the rows of a [n_signals][stride] device array of dtype (VBX_F32|VBX_F64), stride >= n; arithmetic in
+ * fp64.  out: [n_signals] of dtype. */
+VBX_API int vbx_rms(vbx_ctx* ctx, const void* x, int32_t dtype, int64_t n_signals, int32_t n, int64_t stride, void* out);
+VBX_API int vbx_max_amplitude(vbx_ctx* ctx, const void* x, int32_t dtype, int64_t n_signals, int32_t n, int64_t stride,
+                              void* out);
+/* normalize_with_max: x *= 1/max in place; maxes: [n_signals] of dtype, or NULL = normalize() (max_amplitude of the row). */
+VBX_API int vbx_normalize(vbx_ctx* ctx, void* x_inout, int32_t dtype, int64_t n_signals, int32_t n, int64_t stride,
+                          const void* maxes);
+/* preemphasis(factor): y[n-1] = x[n-1], y[i] = x[i] + 2π·factor·y[i+1] in place (anti-causal, additive, as written). */
+VBX_API int vbx_preemphasis(vbx_ctx* ctx, void* x_inout, int32_t dtype, int64_t n_signals, int32_t n, int64_t stride,
+                            double factor);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,6 +213,7 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->windows) cudaFree(kv.second);
+    vbx_mfcc_cache_free(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_start);

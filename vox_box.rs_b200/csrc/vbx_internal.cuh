@@ -15,6 +15,9 @@
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
+struct vbx_mfcc_cache;  // vbx_mfcc.cu: device tables per (N, num_coeffs, bounds, fs)
+void vbx_mfcc_cache_free(struct vbx_ctx* ctx);
+
 struct vbx_ctx {
     int device = 0;
     int sm_count = 0;
@@ -30,6 +33,8 @@ struct vbx_ctx {
     size_t pinned_bytes = 0;
     // window tables (device, f64), keyed by (kind << 32 | n)
     std::map<uint64_t, double*> windows;
+    vbx_mfcc_cache* mfcc_cache = nullptr;
+    bool mfcc_fft_f32 = false;  // MFCC transform precision (default fp64)
 };
 
 int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);

@@ -108,6 +108,16 @@ def _declare(L):
     sig("vbx_pitch_extract", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
     sig("vbx_interpolate_sinc", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp)
     sig("vbx_improve_extremum", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp)
+    sig("vbx_mfcc", C.c_int, _vp, _frp, _i32, _i32, _d, _d, _d, _vp, _vp, _i32)
+    sig("vbx_mfcc_host", C.c_int, _vp, _frp, _i32, _i32, _d, _d, _d, _vp, _i32)
+    sig("vbx_mfcc_set_fft_precision", C.c_int, _vp, _i32)
+    sig("vbx_hz_to_mel", _d, _d)
+    sig("vbx_mel_to_hz", _d, _d)
+    sig("vbx_dct", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
+    sig("vbx_rms", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _vp)
+    sig("vbx_max_amplitude", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _vp)
+    sig("vbx_normalize", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _vp)
+    sig("vbx_preemphasis", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _d)
 
 
 def window_table(window, n):
@@ -471,3 +481,78 @@ Context.pitch_host = _pitch_host
 Context.pitch_extract = _pitch_extract
 Context.interpolate_sinc = _interpolate_sinc
 Context.improve_extremum = _improve_extremum
+
+
+# ---- MFCC and waves.rs helpers (appended to Context) -------------------------------------------------
+def hz_to_mel(hz):
+    return load_library().vbx_hz_to_mel(hz)
+
+
+def mel_to_hz(mel):
+    return load_library().vbx_mel_to_hz(mel)
+
+
+def _mfcc(self, frames, num_coeffs, f_lo, f_hi, fs, n_keep=None, out_dtype=F64, want_energies=False):
+    """spectrum.rs:410-440 mfcc over frames → device array [F][n_keep] (and the log-energies [F][num_coeffs])."""
+    n_keep = num_coeffs if n_keep is None else n_keep
+    out = self.empty((frames.n_frames, n_keep), _NP[out_dtype])
+    en = self.empty((frames.n_frames, num_coeffs), _NP[out_dtype]) if want_energies else None
+    self._check(self.lib.vbx_mfcc(self.h, C.byref(frames), num_coeffs, n_keep, f_lo, f_hi, fs, out.ptr,
+                                  en.ptr if en else None, out_dtype), "vbx_mfcc")
+    return (out, en) if want_energies else out
+
+
+def _mfcc_host(self, audio, n_frames, frame_len, stride, window, num_coeffs, f_lo, f_hi, fs, n_keep=None, out_dtype=F64,
+               frames_per_segment=0, segment_stride=0):
+    audio = np.ascontiguousarray(audio)
+    n_keep = num_coeffs if n_keep is None else n_keep
+    fr = self.frames(audio.ctypes.data, n_frames, frame_len, stride, window, I16 if audio.dtype == np.int16 else F32,
+                     frames_per_segment, segment_stride)
+    out = np.zeros((n_frames, n_keep), dtype=_NP[out_dtype])
+    self._check(self.lib.vbx_mfcc_host(self.h, C.byref(fr), num_coeffs, n_keep, f_lo, f_hi, fs, out.ctypes.data, out_dtype),
+                "vbx_mfcc_host")
+    return out
+
+
+def _dct(self, signal):
+    x = np.atleast_2d(np.ascontiguousarray(signal))
+    d = self.to_device(x)
+    out = self.empty(x.shape, x.dtype)
+    self._check(self.lib.vbx_dct(self.h, d.ptr, _dt_of(x), x.shape[0], x.shape[1], out.ptr), "vbx_dct")
+    return out.to_host()
+
+
+def _rows_op(self, name, x):
+    x = np.atleast_2d(np.ascontiguousarray(x))
+    d = self.to_device(x)
+    out = self.empty((x.shape[0],), x.dtype)
+    self._check(getattr(self.lib, name)(self.h, d.ptr, _dt_of(x), x.shape[0], x.shape[1], x.shape[1], out.ptr), name)
+    return out.to_host()
+
+
+def _normalize(self, x, maxes=None):
+    x = np.atleast_2d(np.ascontiguousarray(x))
+    d = self.to_device(x)
+    m = self.to_device(np.ascontiguousarray(maxes, dtype=x.dtype)) if maxes is not None else None
+    self._check(self.lib.vbx_normalize(self.h, d.ptr, _dt_of(x), x.shape[0], x.shape[1], x.shape[1], m.ptr if m else None),
+                "vbx_normalize")
+    return d.to_host()
+
+
+def _preemphasis(self, x, factor):
+    x = np.atleast_2d(np.ascontiguousarray(x))
+    d = self.to_device(x)
+    self._check(self.lib.vbx_preemphasis(self.h, d.ptr, _dt_of(x), x.shape[0], x.shape[1], x.shape[1], factor),
+                "vbx_preemphasis")
+    return d.to_host()
+
+
+Context.mfcc = _mfcc
+Context.mfcc_set_fft_precision = lambda self, dtype: self._check(self.lib.vbx_mfcc_set_fft_precision(self.h, dtype),
+                                                                 "vbx_mfcc_set_fft_precision")
+Context.mfcc_host = _mfcc_host
+Context.dct = _dct
+Context.rms = lambda self, x: _rows_op(self, "vbx_rms", x)
+Context.max_amplitude = lambda self, x: _rows_op(self, "vbx_max_amplitude", x)
+Context.normalize = _normalize
+Context.preemphasis = _preemphasis
