@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py — throughput of the vox_box hot path on B200 (BASELINE.json metric: frames/sec).
 
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5] [--utts U]
+
 Default workload = BASELINE.json configs[1] ("C2"): LPC order-12 autocorrelation + Levinson on 1 h of
 synthetic 16 kHz audio per GPU, 25 ms / 10 ms frames (N=400, hop=160, symmetric Hann), 360 utterances x
-10 s = 359 280 frames.  A "step" is one pass of the hot path over that batch.  One process per GPU; the
-path shards by utterance with no data-path collective (weak scaling: every rank owns its own hour).
-
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
+10 s = 359 280 frames.  A "step" is one pass of the hot path over that batch.  The other configs
+(c3 formants, c4 pitch, c5 MFCC) are the remaining BASELINE.json shapes, on a per-GPU batch that fits
+a quick run (stated in config.workload).  One process per GPU; the path shards by utterance with no
+data-path collective (weak scaling: every rank owns its own batch; torch.distributed/NCCL is used only
+for the barrier and the max-over-ranks of the timing).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events on the library's
 stream, max over ranks); `e2e` = the same work through the host-pointer C-ABI call (pinned host buffers,
-H2D + kernels + D2H inside the timed region); `roofline` = the dominant kernel against its bounding pipe;
-`cpu_baseline` = the CPU oracle (a C++ port of the Rust reference — no Rust toolchain in this image)
-timed on this box's host cores.  `--impl reference` times that CPU port alone.
+H2D + kernels + D2H inside the timed region); `roofline` = the dominant kernel against the pipe that
+bounds it (measured on this device in this run) and `roofline_hbm` the same against MEASURED_PEAKS.json's
+HBM number; `cpu_baseline` = the CPU oracle (a C++ port of the Rust reference — there is no Rust
+toolchain in this image) timed on this box's host cores.  `--impl reference` times that CPU port alone.
 """
 import argparse
+import ctypes as C
 import json
 import os
+import re
 import sys
 import threading
 import time
@@ -27,17 +33,47 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "vox_box.rs_b200", "python"))
 sys.path.insert(0, ROOT)
 
+MALE = (320., 1440., 2760., 3200.)  # lib.rs:27
+
 CONFIGS = {
-    # name: fs, N, hop, utterance seconds, utterances per GPU, description
-    "c2": dict(fs=16000, n=400, hop=160, seconds=10.0, utts=360, p=12,
+    "c2": dict(kind="lpc", fs=16000, n=400, hop=160, seconds=10.0, utts=360, distinct=360, p=12,
+               metric="LPC-12 frames/sec (autocorrelation + Levinson)", dtype="f64",
                workload="C2: LPC-12 (Hann -> autocorrelate(13) fp64 -> Levinson) on 1 h synthetic 16 kHz audio, "
-                        "N=400 hop=160, 360 utt x 998 frames = 359280 frames per GPU"),
+                        "N=400 hop=160, {utts} utt x {J} frames = {F} frames per GPU"),
+    "c3": dict(kind="formants", fs=44100, n=1102, hop=441, seconds=10.0, utts=1125, distinct=24, p=12,
+               metric="LPC-12 + formant frames/sec (autocorrelation + Levinson -> Laguerre roots -> McCandless)", dtype="f64",
+               workload="C3: formant extraction (Hann -> autocorrelate(13) -> Levinson -> Laguerre roots -> resonances -> "
+                        "McCandless tracker) on synthetic 44.1 kHz speech, N=1102 hop=441, {utts} utt x {J} frames = {F} frames "
+                        "per GPU per step (a quarter of the 4500-utterance per-GPU share of 100 h over 8 GPUs; "
+                        "{distinct} distinct utterances tiled)"),
+    "c4": dict(kind="pitch", fs=16000, n=640, hop=160, seconds=10.0, utts=360, distinct=48,
+               metric="Boersma pitch frames/sec (75-600 Hz)", dtype="f32 lag sweep + f64 refinement",
+               workload="C4: Boersma pitch 75-600 Hz (Hann -> all-lag autocorrelation -> candidates -> Brent/sinc refinement) "
+                        "on synthetic 16 kHz audio, N=640 hop=160, {utts} utt x {J} frames = {F} frames per GPU per step "
+                        "(1 h of the 1000 h corpus per step; {distinct} distinct utterances tiled)"),
+    "c5": dict(kind="mfcc", fs=16000, n=400, hop=160, seconds=10.0, utts=3600, distinct=48,
+               metric="MFCC frames/sec (13 coefficients from 40 mel bands)", dtype="f64",
+               workload="C5: MFCC (Hann -> FFT -> 40 mel bands -> log10 -> DCT, 13 kept) on synthetic 16 kHz audio, N=400 "
+                        "hop=160, {utts} utt x {J} frames = {F} frames per GPU per step ({distinct} distinct utterances tiled)"),
 }
 
 
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def _ncu_traffic(profile_name):
+    """dram read+write bytes per launch from a committed `ncu --set full` summary under profiles/ (or None)."""
+    try:
+        txt = open(os.path.join(ROOT, "profiles", profile_name)).read()
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(key + r" = ([0-9.]+) (\w+)", txt)
+            tot += float(m.group(1)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+        return tot
     except Exception:
         return None
 
@@ -119,8 +155,52 @@ class ClockSampler:
 
 
 def make_corpus(cfg, rank):
+    """[utts, n_samples] fp32: `distinct` synthetic utterances (seeded by rank) tiled to `utts` rows."""
     from voxbox_b200 import synth
-    return synth.corpus(cfg["utts"], cfg["fs"], cfg["seconds"], first=rank * cfg["utts"])
+    distinct = min(cfg["distinct"], cfg["utts"])
+    base = synth.corpus(distinct, cfg["fs"], cfg["seconds"], first=rank * distinct)
+    reps = -(-cfg["utts"] // distinct)
+    return np.ascontiguousarray(np.tile(base, (reps, 1))[:cfg["utts"]])
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) of each config: used by --impl reference and by the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def cpu_pass(cfg, audio_rows, J, n_threads):
+    """One pass of the reference's per-frame loop over the given utterances on the CPU oracle."""
+    import oracle
+    N, hop, fs = cfg["n"], cfg["hop"], float(cfg["fs"])
+    kind = cfg["kind"]
+    for row in audio_rows:
+        if kind == "lpc":
+            oracle.batch_lpc(row, J, N, hop, oracle.WIN_HANN_SYMMETRIC, cfg["p"], n_threads=n_threads)
+        elif kind == "pitch":
+            oracle.batch_pitch(row, J, N, hop, oracle.WIN_HANN_SYMMETRIC, fs, 0.45, 75.0, 600.0, 16, n_threads=n_threads)
+        elif kind == "mfcc":
+            oracle.batch_mfcc(row, J, N, hop, oracle.WIN_HANN_SYMMETRIC, 40, 133.0, 6855.0, fs, n_keep=13, n_threads=n_threads)
+    if kind == "formants":
+        # utterances in parallel (the tracker is sequential inside an utterance); frame f of the flattened batch
+        # starts at f*hop, so utterance u owns frames [u*ns/hop, u*ns/hop + J) when hop divides the utterance length
+        rows = np.ascontiguousarray(np.stack(audio_rows))
+        U, ns = rows.shape
+        est = np.array([[f, 1.0] for f in MALE])
+        if ns % hop == 0:
+            # ranges [start_u, start_u + J) are the utterances; the 1-2 frames that straddle two utterances in between
+            # are walked as (negligible) extra ranges because the oracle's batch loop takes contiguous frame ranges
+            starts = np.arange(U, dtype=np.int64) * (ns // hop)
+            offs = np.stack([starts, starts + J], axis=1).reshape(-1)
+            oracle.batch_formants(rows.reshape(-1), int(offs[-1]), N, hop, oracle.WIN_HANN_SYMMETRIC, 1, fs, cfg["p"], offs, est,
+                                  n_threads=n_threads)
+        else:
+            for u in range(U):
+                oracle.batch_formants(rows[u], J, N, hop, oracle.WIN_HANN_SYMMETRIC, 1, fs, cfg["p"],
+                                      np.array([0, J], dtype=np.int64), est, n_threads=n_threads)
+
+
+def cpu_sample_utts(cfg, threads):
+    """Utterances per bounded CPU sample (about 3-10 s of CPU work on `threads` cores)."""
+    per_thread = {"lpc": 20, "formants": 2, "pitch": 1, "mfcc": 6}[cfg["kind"]]
+    return max(1, min(cfg["utts"], per_thread * max(1, threads)))
 
 
 def run_reference(args, cfg, rank, world):
@@ -130,69 +210,188 @@ def run_reference(args, cfg, rank, world):
         return
     import oracle
     oracle.build()
-    audio = make_corpus(cfg, 0)
-    n_samp = audio.shape[1]
-    J = oracle.n_frames_of(n_samp, cfg["n"], cfg["hop"])
-    # bounded sample: 36 utterances (1/10 of the hour) per step, all host threads
-    sample_utts = min(cfg["utts"], 36)
     threads = oracle.max_threads()
-
-    def step():
-        for u in range(sample_utts):
-            oracle.batch_lpc(audio[u], J, cfg["n"], cfg["hop"], oracle.WIN_HANN_SYMMETRIC, cfg["p"], n_threads=0)
+    sub = dict(cfg)
+    sub["utts"] = sub["distinct"] = cpu_sample_utts(cfg, threads)
+    audio = make_corpus(sub, 0)
+    J = oracle.n_frames_of(audio.shape[1], cfg["n"], cfg["hop"])
+    rows = list(audio)
 
     for _ in range(args.warmup):
-        step()
+        cpu_pass(cfg, rows, J, 0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cpu_pass(cfg, rows, J, 0)
     dt = time.perf_counter() - t0
-    frames = sample_utts * J * args.steps
+    frames = len(rows) * J * args.steps
     value = frames / dt
+    full = dict(cfg)
+    Jf = J
     line = {
-        "impl": "reference", "metric": "LPC-12 frames/sec (autocorrelation + Levinson)", "value": value,
+        "impl": "reference", "metric": cfg["metric"], "value": value,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "sample": f"{sample_utts} of {cfg['utts']} utterances per step"},
+        "config": {"workload": cfg["workload"].format(utts=full["utts"], J=Jf, F=full["utts"] * Jf, distinct=full["distinct"]),
+                   "sample": f"{len(rows)} of {cfg['utts']} utterances per step"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_utts} utterances x {J} frames per step, {args.steps} steps, OpenMP over frames"},
+                         "sample": f"C++ f64 port of the Rust reference (no cargo in this image): {len(rows)} utterances x {J} "
+                                   f"frames per step, {args.steps} steps, OpenMP over frames on {threads} threads"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(cfg, audio):
+def cpu_baseline(cfg, rank_audio):
     """Bounded CPU sample on rank 0 (N=1 only): oracle port, single thread as shipped + all threads."""
     import oracle
     oracle.build()
-    n_samp = audio.shape[1]
-    J = oracle.n_frames_of(n_samp, cfg["n"], cfg["hop"])
+    J = oracle.n_frames_of(rank_audio.shape[1], cfg["n"], cfg["hop"])
     threads = oracle.max_threads()
-    one_utts, all_utts = 20, min(cfg["utts"], 20 * max(1, threads))
+    n_all = min(cpu_sample_utts(cfg, threads), rank_audio.shape[0])
+    n_one = max(1, min(n_all, {"lpc": 20, "formants": 3, "pitch": 1, "mfcc": 6}[cfg["kind"]]))
+    rows = list(rank_audio[:n_all])
     t0 = time.perf_counter()
-    for u in range(one_utts):
-        oracle.batch_lpc(audio[u], J, cfg["n"], cfg["hop"], oracle.WIN_HANN_SYMMETRIC, cfg["p"], n_threads=1)
+    cpu_pass(cfg, rows[:n_one], J, 1)
     t1 = time.perf_counter() - t0
     reps = 0
     t0 = time.perf_counter()
     while True:
-        for u in range(all_utts):
-            oracle.batch_lpc(audio[u], J, cfg["n"], cfg["hop"], oracle.WIN_HANN_SYMMETRIC, cfg["p"], n_threads=0)
+        cpu_pass(cfg, rows, J, 0)
         reps += 1
         if time.perf_counter() - t0 > 3.0 or reps >= 50:
             break
     tn = time.perf_counter() - t0
-    return {"value": all_utts * J * reps / tn, "unit": "frames/s", "cores": threads, "kind": "port",
-            "single_thread_value": one_utts * J / t1,
-            "sample": f"C++ f64 port of the Rust reference (no cargo here): {all_utts} utterances x {J} frames x {reps} "
-                      f"passes on {threads} OpenMP threads; single thread: {one_utts} utterances"}
+    return {"value": n_all * J * reps / tn, "unit": "frames/s", "cores": threads, "kind": "port",
+            "single_thread_value": n_one * J / t1,
+            "sample": f"C++ f64 port of the Rust reference (no cargo here): {n_all} utterances x {J} frames x {reps} "
+                      f"passes on {threads} OpenMP threads; single thread: {n_one} utterances"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """Device buffers + the device-pointer step and the host-pointer (e2e) step of one config."""
+
+    def __init__(self, ctx, vb, cfg, audio):
+        self.ctx, self.vb, self.cfg = ctx, vb, cfg
+        L, h = ctx.lib, ctx.h
+        U, ns = audio.shape
+        N, hop, fs = cfg["n"], cfg["hop"], float(cfg["fs"])
+        J = ctx.n_frames_of(ns, N, hop)
+        F = U * J
+        self.U, self.J, self.F, self.ns = U, J, F, ns
+        self.d_audio = ctx.to_device(audio)
+        win = vb.WINDOW_HANN_SYMMETRIC
+        fr = ctx.frames(self.d_audio.ptr, F, N, hop, win, frames_per_segment=J, segment_stride=ns)
+        self.h_in = C.c_void_p()
+        ctx._check(L.vbx_malloc_host(h, audio.nbytes, C.byref(self.h_in)), "vbx_malloc_host")
+        np.ctypeslib.as_array(C.cast(self.h_in, C.POINTER(C.c_float)), shape=audio.shape)[...] = audio
+        hfr = ctx.frames(self.h_in.value, F, N, hop, win, frames_per_segment=J, segment_stride=ns)
+        self.h2d = int(audio.nbytes)
+        kind = cfg["kind"]
+
+        def pinned(nbytes):
+            p = C.c_void_p()
+            ctx._check(L.vbx_malloc_host(h, nbytes, C.byref(p)), "vbx_malloc_host")
+            return p
+
+        if kind == "lpc":
+            p = cfg["p"]
+            d_r, d_ac = ctx.empty((F, p + 1), np.float32), ctx.empty((F, p + 1), np.float32)
+            out_bytes = F * (p + 1) * 4
+            h_r, h_ac = pinned(out_bytes), pinned(out_bytes)
+            self.step = lambda: ctx._check(L.vbx_lpc(h, C.byref(fr), p, d_r.ptr, d_ac.ptr, None, vb.F32), "vbx_lpc")
+            self.e2e_step = lambda: ctx._check(L.vbx_lpc_host(h, C.byref(hfr), p, h_r, h_ac, None, vb.F32), "vbx_lpc_host")
+            self.d2h = 2 * out_bytes
+            self.api = "vbx_lpc_host (pinned host buffers)"
+            self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_r, C.POINTER(C.c_float)), shape=(F, p + 1))[::max(1, F // 1000), 0], dtype=np.float64))
+            self.outputs = "r[13], ac[13] fp32"
+            self._keep = (d_r, d_ac)
+        elif kind == "formants":
+            p = cfg["p"]
+            est0 = np.tile(np.array([[f, 1.0] for f in MALE], dtype=np.float32), (U, 1, 1))
+            d_est0 = ctx.to_device(est0)
+            d_est = ctx.empty((U, 4, 2), np.float32)
+            d_trk = ctx.empty((F, 4, 2), np.float32)
+            trk_bytes = F * 4 * 2 * 4
+            h_trk, h_est = pinned(trk_bytes), pinned(est0.nbytes)
+
+            def step():
+                # the tracker state is in/out: every step starts from the MALE estimates (tests/lib.rs:36,60)
+                ctx._check(L.vbx_memcpy_d2d(h, d_est.ptr, d_est0.ptr, est0.nbytes), "vbx_memcpy_d2d")
+                ctx._check(L.vbx_find_formants(h, C.byref(fr), fs, p, vb.LPC_AUTOCORR, d_est.ptr, 4, d_trk.ptr, None, None, None,
+                                               vb.F32), "vbx_find_formants")
+
+            def e2e_step():
+                C.memmove(h_est, est0.ctypes.data, est0.nbytes)
+                ctx._check(L.vbx_find_formants_host(h, C.byref(hfr), fs, p, vb.LPC_AUTOCORR, h_est, 4, h_trk, None, None, None,
+                                                    vb.F32), "vbx_find_formants_host")
+
+            self.step, self.e2e_step = step, e2e_step
+            self.h2d += int(est0.nbytes)
+            self.d2h = trk_bytes + int(est0.nbytes)
+            self.api = "vbx_find_formants_host (pinned host buffers)"
+            self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_trk, C.POINTER(C.c_float)), shape=(F, 8))[::max(1, F // 1000)], dtype=np.float64))
+            self.outputs = "4 formant (frequency, bandwidth) tracks per frame, fp32"
+            self._keep = (d_est0, d_est, d_trk, est0)
+        elif kind == "pitch":
+            K = 16
+            d_c, d_n, d_s = ctx.empty((F, K, 2), np.float32), ctx.empty((F,), np.int32), ctx.empty((F,), np.uint8)
+            h_c, h_n, h_s = pinned(F * K * 8), pinned(F * 4), pinned(F)
+            self.step = lambda: ctx._check(L.vbx_pitch(h, C.byref(fr), fs, 0.45, 75.0, 600.0, K, d_c.ptr, d_n.ptr, d_s.ptr, vb.F32), "vbx_pitch")
+            self.e2e_step = lambda: ctx._check(L.vbx_pitch_host(h, C.byref(hfr), fs, 0.45, 75.0, 600.0, K, h_c, h_n, h_s, vb.F32), "vbx_pitch_host")
+            self.d2h = F * (K * 8 + 5)
+            self.api = "vbx_pitch_host (pinned host buffers)"
+            self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_c, C.POINTER(C.c_float)), shape=(F, K * 2))[::max(1, F // 1000), 0], dtype=np.float64))
+            self.outputs = "up to 16 (frequency, strength) candidates per frame fp32 + count + status"
+            self._keep = (d_c, d_n, d_s)
+        elif kind == "mfcc":
+            d_o = ctx.empty((F, 13), np.float32)
+            h_o = pinned(F * 13 * 4)
+            self.step = lambda: ctx._check(L.vbx_mfcc(h, C.byref(fr), 40, 13, 133.0, 6855.0, fs, d_o.ptr, None, vb.F32), "vbx_mfcc")
+            self.e2e_step = lambda: ctx._check(L.vbx_mfcc_host(h, C.byref(hfr), 40, 13, 133.0, 6855.0, fs, h_o, vb.F32), "vbx_mfcc_host")
+            self.d2h = F * 13 * 4
+            self.api = "vbx_mfcc_host (pinned host buffers)"
+            self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_o, C.POINTER(C.c_float)), shape=(F, 13))[::max(1, F // 1000), 0], dtype=np.float64))
+            self.outputs = "13 MFCC per frame fp32"
+            self._keep = (d_o,)
+
+    def roofline(self, frames_per_s, peaks, hbm_peak, hbm_src):
+        """Dominant kernel of the step against the pipe that bounds it + the HBM view."""
+        cfg, N, hop = self.cfg, self.cfg["n"], self.cfg["hop"]
+        kind = cfg["kind"]
+        if kind == "lpc":
+            p = cfg["p"]
+            flop, pipe, kern, prof = 2 * (p + 1) * N + N + 350, "fp64", "lpc_fused_kernel<13,float>", "r1_lpc_fused_v1_full.txt"
+            byts = 4 * hop + 2 * 4 * (p + 1)
+        elif kind == "formants":
+            p = cfg["p"]
+            # SURVEY §8d C3 path A: lag MACs + window + Levinson (fp64) | roots 10·20·(3·12·8+60) (fp32) | resonances
+            flop, pipe, kern, prof = 2 * (p + 1) * N + N + 350, "fp64", "lpc_fused_kernel<13,float> (+ lpc_roots_kernel fp32, tracker_kernel)", None
+            byts = 4 * hop + 4 * 2 * 4
+        elif kind == "pitch":
+            # SURVEY §8d C4: 410 k flop lag sweep (fp32) + ~2.5 M flop Brent/sinc refinement (fp64), the dominant kernel
+            flop, pipe, kern, prof = 2.5e6, "fp64", "pitch_refine_kernel", "r1_refine_v0_full.txt"
+            byts = 4 * hop + 140
+        else:
+            # SURVEY §8d C5: 5·N·log2(N) complex FFT + band MACs + 40 log10 + 2·13·40 DCT ≈ 19.5 k flop
+            flop, pipe, kern, prof = 19.5e3, "fp64", "mfcc_kernel<float,double>", "r1_mfcc_v0_full.txt"
+            byts = 4 * hop + 4 * 13
+        peak = peaks[pipe + "_tflops"]
+        ach = flop * frames_per_s / 1e12
+        ach_gb = byts * frames_per_s / 1e9
+        return ({"bound": pipe, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                 "traffic": _ncu_traffic(prof) if prof else None, "kernel": kern, "flop_per_frame": flop,
+                 "peak_source": "vbx_measure_peaks: dependent-free FMA loop on this device, this run",
+                 "note": "whole-step time used for the dominant kernel (its share of the step is in profiles/)"},
+                {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                 "bytes_per_frame": byts, "peak_source": hbm_src})
 
 
 def run_ours(args, cfg, rank, world, local_rank):
-    import ctypes as C
-
     import voxbox_b200 as vb
     dist = None
     if world > 1:
@@ -213,93 +412,61 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ctx = vb.Context(local_rank)
+    ctx = vb.Context(local_rank)  # raises without the CUDA library / a device: no CPU fallback
     audio = make_corpus(cfg, rank)
-    U, n_samp = audio.shape
-    N, hop, p = cfg["n"], cfg["hop"], cfg["p"]
-    J = ctx.n_frames_of(n_samp, N, hop)
-    F = U * J
-    d_audio = ctx.to_device(audio)
-    d_r = ctx.empty((F, p + 1), np.float32)
-    d_ac = ctx.empty((F, p + 1), np.float32)
-    fr = ctx.frames(d_audio.ptr, F, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=n_samp)
-
-    def step():
-        ctx._check(ctx.lib.vbx_lpc(ctx.h, C.byref(fr), p, d_r.ptr, d_ac.ptr, None, vb.F32), "vbx_lpc")
+    wl = Workload(ctx, vb, cfg, audio)
+    F = wl.F
+    warmup = max(args.warmup, 3)
 
     peaks = ctx.measure_peaks()  # FP32/FP64 FMA pipe peaks of this device (roofline denominators)
     with ClockSampler(local_rank) as clocks:
         # ---- device-resident throughput -------------------------------------------------------
-        for _ in range(max(args.warmup, 3)):
-            step()
+        for _ in range(warmup):
+            wl.step()
         ctx.sync()
         barrier()
         l0 = ctx.kernel_launches
         ctx.timer_start()
         for _ in range(args.steps):
-            step()
+            wl.step()
         ms = ctx.timer_stop_ms()
         launches = ctx.kernel_launches - l0
         barrier()
         ms = max_over_ranks(ms)
 
         # ---- end to end through the host-pointer C-ABI call ------------------------------------------
-        h_in = C.c_void_p()
-        ctx._check(ctx.lib.vbx_malloc_host(ctx.h, audio.nbytes, C.byref(h_in)), "vbx_malloc_host")
-        h_audio = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=audio.shape)
-        h_audio[...] = audio
-        out_bytes = F * (p + 1) * 4
-        h_out = [C.c_void_p(), C.c_void_p()]
-        for h in h_out:
-            ctx._check(ctx.lib.vbx_malloc_host(ctx.h, out_bytes, C.byref(h)), "vbx_malloc_host")
-        hfr = ctx.frames(h_in.value, F, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=n_samp)
-
-        def e2e_step():
-            ctx._check(ctx.lib.vbx_lpc_host(ctx.h, C.byref(hfr), p, h_out[0], h_out[1], None, vb.F32), "vbx_lpc_host")
-
         e2e_steps = max(3, min(args.steps, 20))
         for _ in range(3):
-            e2e_step()
+            wl.e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            e2e_step()
+            wl.e2e_step()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
-    h_r = np.ctypeslib.as_array(C.cast(h_out[0], C.POINTER(C.c_float)), shape=(F, p + 1))
-    checksum = float(np.sum(h_r[:: max(1, F // 1000), 0], dtype=np.float64))
+    checksum = wl.check()
 
     if rank == 0:
         total_frames = F * world
         value = total_frames * args.steps / (ms * 1e-3)
-        # roofline of the dominant (only) kernel, lpc_fused_kernel<13,float>: FP64-pipe bound.
-        # Algorithmic work per frame: 2·13·400 lag MACs + 400 window + ~350 Levinson = 11 150 flop,
-        # 744 B (4·hop in, 2·13·4 out).
-        flop_per_frame = 2 * (p + 1) * N + N + 350
-        bytes_per_frame = 4 * hop + 2 * 4 * (p + 1)
-        kernel_s = ms * 1e-3 / args.steps
-        ach_tf = flop_per_frame * F / kernel_s / 1e12
-        ach_gb = bytes_per_frame * F / kernel_s / 1e9
         mp = _peaks()
         hbm_peak = mp["hbm_gbs"] if mp else 6650.0
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if mp else "fallback 6650 GB/s (of fallback)"
+        roof, roof_hbm = wl.roofline(F * args.steps / (ms * 1e-3), peaks, hbm_peak, hbm_src)
+        in_mb = audio.nbytes / 1e6
         line = {
-            "metric": "LPC-12 frames/sec (autocorrelation + Levinson)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "frames_per_gpu": F, "order": p, "window": "hann_symmetric",
-                       "outputs": "r[13], ac[13] fp32", "l2": "inputs larger than L2 (230 MB audio per step), no flush",
+            "metric": cfg["metric"], "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": cfg["workload"].format(utts=wl.U, J=wl.J, F=F, distinct=min(cfg["distinct"], wl.U)),
+                       "frames_per_gpu": F, "window": "hann_symmetric", "outputs": wl.outputs,
+                       "l2": f"inputs larger than L2 ({in_mb:.0f} MB audio per step), no flush" if in_mb > 130 else
+                             f"inputs ({in_mb:.0f} MB) fit L2: compute-bound kernels, no flush",
                        "parallelism": f"utterance-sharded x{world}, no collective"},
-            "e2e": {"value": total_frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(audio.nbytes),
-                    "d2h_bytes_per_step": int(2 * out_bytes), "steps": e2e_steps, "api": "vbx_lpc_host (pinned host buffers)"},
+            "e2e": {"value": total_frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d,
+                    "d2h_bytes_per_step": int(wl.d2h), "steps": e2e_steps, "api": wl.api},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
-                         "frac": ach_tf / peaks["fp64_tflops"], "traffic": None,
-                         "kernel": "lpc_fused_kernel<13,float>", "flop_per_frame": flop_per_frame,
-                         "peak_source": "vbx_measure_peaks: DFMA loop on this device, this run"},
-            "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gb / hbm_peak, "bytes_per_frame": bytes_per_frame,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if mp else "fallback 6650 (of fallback)"},
-            "pipe_peaks": peaks,
+            "roofline": roof, "roofline_hbm": roof_hbm, "pipe_peaks": peaks,
             "clocks": clocks.summary(),
             "checksum": checksum,
         }
@@ -314,16 +481,21 @@ def run_ours(args, cfg, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--utts", type=int, default=None, help="utterances per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.utts:
+        cfg["utts"] = args.utts
+    if args.steps is None:
+        args.steps = {"lpc": 200, "formants": 20, "pitch": 5, "mfcc": 20}[cfg["kind"]] if args.impl == "ours" else 3
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
     else:

@@ -121,6 +121,7 @@ VBX_API int vbx_malloc_host(vbx_ctx* ctx, size_t bytes, void** host_out); /* pin
 VBX_API int vbx_free_host(vbx_ctx* ctx, void* host);
 VBX_API int vbx_memcpy_h2d(vbx_ctx* ctx, void* dev, const void* host, size_t bytes); /* async on ctx stream */
 VBX_API int vbx_memcpy_d2h(vbx_ctx* ctx, void* host, const void* dev, size_t bytes); /* async on ctx stream */
+VBX_API int vbx_memcpy_d2d(vbx_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 VBX_API int vbx_memset(vbx_ctx* ctx, void* dev, int value, size_t bytes);
 
 /* Device timing on the context's stream (CUDA events), for callers without a CUDA binding. */

@@ -277,6 +277,11 @@ int vbx_memcpy_d2h(vbx_ctx* ctx, void* host, const void* dev, size_t bytes) {
     if (bytes) VBX_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return VBX_OK;
 }
+int vbx_memcpy_d2d(vbx_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return VBX_ERR_BADARG;
+    if (bytes) VBX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return VBX_OK;
+}
 int vbx_memset(vbx_ctx* ctx, void* dev, int value, size_t bytes) {
     if (!ctx) return VBX_ERR_BADARG;
     if (bytes) VBX_CUDA(ctx, cudaMemsetAsync(dev, value, bytes, ctx->stream));

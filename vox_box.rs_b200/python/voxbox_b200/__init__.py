@@ -79,6 +79,7 @@ def _declare(L):
     sig("vbx_free_host", C.c_int, _vp, _vp)
     sig("vbx_memcpy_h2d", C.c_int, _vp, _vp, _vp, _sz)
     sig("vbx_memcpy_d2h", C.c_int, _vp, _vp, _vp, _sz)
+    sig("vbx_memcpy_d2d", C.c_int, _vp, _vp, _vp, _sz)
     sig("vbx_memset", C.c_int, _vp, _vp, C.c_int, _sz)
     sig("vbx_timer_start", C.c_int, _vp)
     sig("vbx_timer_stop_ms", C.c_int, _vp, C.POINTER(C.c_float))
