@@ -391,6 +391,174 @@ __global__ void __launch_bounds__(256) pitch_refine_kernel(const PitchParams P) 
     }
 }
 
+// K7 (v1): four candidates per warp, 8 lanes each, in lockstep.
+//
+// Lane ℓ8 of a slot owns the terms n ≡ ℓ8 (mod 8) of both sides of interpolate_sinc's sum, so that per term
+//   * (−1)ⁿ is a per-lane constant (stride 8 is even),
+//   * the Hann factor ½ + ½cos(π(φ+n)/(φ+D)) advances by a fixed rotation (cos 8δ, sin 8δ), δ = π/(φ+D),
+//   * the two sides share one reciprocal: y_l·h_l/t_l + y_r·h_r/t_r = (y_l·h_l·t_r + y_r·h_r·t_l)/(t_l·t_r).
+// The four slots of a warp hold consecutive work-list entries (same frame, ascending lag, hence similar depth D)
+// and run Brent in lockstep; the term loop runs to the largest D of the four, shorter slots are masked.
+// Brent's state is replicated in the 8 lanes of a slot (identical arithmetic ⇒ identical values), the only
+// cross-lane traffic is the 3-step butterfly that sums the 8 partial sums.
+__device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positive x: MUFU seed + 2 Newton steps
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+__global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)*P.counter;
+    const long long n_groups = (total + 3) >> 2;
+    const int N = P.n;
+    const int offset = -P.ixmax - 1;
+    const int nx = P.ixmax - offset;
+    const int ylen = 2 * N;
+    const double golden = 1. - 0.6180339887498948482045868343656381177203091798057628621;
+    const double EPS = 2.220446049250313e-16, sqrt_epsilon = 1.4901161193847656e-08, tol = 1e-10;
+    const double sgn = (l8 & 1) ? -1.0 : 1.0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (long long g = warp_global; g < n_groups; g += n_warps) {
+        const long long e = 4 * g + sub;
+        const bool valid = e < total;
+        PitchCand cd;
+        cd.frame = 0; cd.k = 0; cd.n = 0.0;
+        if (valid) cd = P.list[e];
+        const double* __restrict__ y = P.y + (size_t)cd.frame * N;
+        auto yat = [&](int idx) -> double { return (idx >= 0 && idx < N) ? __ldg(y + idx) : 0.0; };  // zero-extended to 2N
+        // improve_extremum's early returns (periodic.rs:193-194)
+        bool done = !valid;
+        double rx = 0., ry = 0.;
+        const double ixmid = cd.n;
+        if (valid) {
+            if (ixmid == 0.) { rx = 0.; ry = yat(0); done = true; }
+            else if (ixmid >= (double)nx) { rx = (double)nx; ry = yat(nx - 1); done = true; }
+        }
+        // brent_maximize(f, (ixmid−1, ixmid+1), tol = 1e-10)
+        double a = ixmid - 1., b = ixmid + 1.;
+        double v = a + golden * (b - a), w = v, x = v, fv = 0., fw = 0., fx = 0.;
+        double t = v;
+        int iter = 0;  // 0: the initial evaluation is pending
+        while (!__all_sync(FULL, done)) {
+            // ---- interpolate_sinc(y, offset, nx, t, 1200): per-slot setup ----------------------------------------
+            const double fl = floor(t);
+            const int nl = (fl > 0.0) ? (int)fmin(fl, 1.0e9) : 0;
+            const int nr = nl + 1;
+            const double phil = t - (double)nl, phir = 1. - phil;
+            bool special = done;
+            double sval = 0.;
+            int D = -1;
+            if (!done) {
+                if (t > (double)nx) { special = true; const int i = offset + nx - 1; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else if (t < 0.) { special = true; sval = yat(0); }
+                else if (fabs(t - (double)nl) < 1.0e-10) { special = true; const int i = offset + nl; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else if (fabs(t - (double)nr) < 1.0e-10) { special = true; const int i = offset + nr; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else {
+                    int md = 1200;
+                    if (offset + nr < md) md = (offset + nr < 0) ? 0 : offset + nr;
+                    if (offset + nl + md >= nx) md = nx - offset + nl - 1;
+                    D = md;
+                }
+            }
+            const bool act = !special;
+            const double pl = act ? phil : 0.5, pr = act ? phir : 0.5;
+            const double Dd = (double)(D < 0 ? 0 : D);
+            const double inv_l = 1.0 / (pl + Dd), inv_r = 1.0 / (pr + Dd);
+            double s0, c_unused;
+            sincospi(pl, &s0, &c_unused);
+            double S8l, C8l, S8r, C8r, sl, cl, sr, cr;
+            sincospi(8.0 * inv_l, &S8l, &C8l);
+            sincospi(8.0 * inv_r, &S8r, &C8r);
+            double tl = pl + (double)l8, tr = pr + (double)l8;
+            sincospi(tl * inv_l, &sl, &cl);
+            sincospi(tr * inv_r, &sr, &cr);
+            const int L = offset + nr, R = offset + nl;
+            const int Dmax = __reduce_max_sync(FULL, D);
+            double acc = 0.;
+            for (int n = l8; n <= Dmax; n += 8) {
+                const bool on = (n <= D);
+                int il = L - n;
+                il = il < 0 ? 0 : il;
+                int ir = R + n;
+                ir = ir < 0 ? 0 : ir;
+                const double yl = (on && il < N) ? __ldg(y + il) : 0.0;
+                const double yr = (on && ir < N) ? __ldg(y + ir) : 0.0;
+                const double hl = fma(0.5, cl, 0.5), hr = fma(0.5, cr, 0.5);
+                const double num = fma(yl * hl, tr, (yr * hr) * tl);
+                acc = fma(num, rcp_pos(tl * tr), acc);
+                // advance: t += 8, rotate the Hann phase by 8δ
+                const double ncl = fma(cl, C8l, -(sl * S8l)), nsl = fma(sl, C8l, cl * S8l);
+                const double ncr = fma(cr, C8r, -(sr * S8r)), nsr = fma(sr, C8r, cr * S8r);
+                cl = ncl; sl = nsl; cr = ncr; sr = nsr;
+                tl += 8.0; tr += 8.0;
+            }
+            acc *= sgn;
+            acc += __shfl_xor_sync(FULL, acc, 1);
+            acc += __shfl_xor_sync(FULL, acc, 2);
+            acc += __shfl_xor_sync(FULL, acc, 4);
+            const double ft = special ? sval : acc * (s0 * (1.0 / kPi));
+            // ---- Brent update (periodic.rs:121-186) ---------------------------------------------------------------------
+            if (!done) {
+                if (iter == 0) {
+                    fv = ft; fx = ft; fw = ft;
+                    iter = 1;
+                } else {
+                    if (ft <= fx) {
+                        if (t < x) b = x; else a = x;
+                        v = w; w = x; x = t;
+                        fv = fw; fw = fx; fx = ft;
+                    } else {
+                        if (t < x) a = t; else b = t;
+                        if (ft <= fw || fabs(w - x) < EPS) {
+                            v = w; w = t;
+                            fv = fw; fw = ft;
+                        } else if (ft <= fv || fabs(v - x) < EPS || fabs(v - w) < EPS) {
+                            v = t;
+                            fv = ft;
+                        }
+                    }
+                    ++iter;
+                }
+                if (iter > 60) {
+                    done = true; rx = x; ry = fx;
+                } else {
+                    const double range = b - a, middle_range = (a + b) * 0.5;
+                    const double tol_act = sqrt_epsilon * fabs(x) + tol / 3.;
+                    if (fabs(x - middle_range) + range * 0.5 <= 2. * tol_act) {
+                        done = true; rx = x; ry = fx;
+                    } else {
+                        double new_step = (x < middle_range) ? golden * (b - x) : golden * (a - x);
+                        if (fabs(x - w) >= tol_act) {
+                            const double tt = (x - w) * (fx - fv);
+                            double q = (x - v) * (fx - fw);
+                            double p = (x - v) * q - (x - w) * tt;
+                            q = 2. * q - tt;
+                            if (q > 0.) p = -p; else q = -q;
+                            if (fabs(p) < fabs(new_step * q) && p > q * (a - x + 2. * tol_act) && p < q * (b - x - 2. * tol_act))
+                                new_step = p / q;
+                        }
+                        if (fabs(new_step) < tol_act) new_step = (new_step > 0.) ? tol_act : -tol_act;
+                        t = x + new_step;
+                    }
+                }
+            }
+        }
+        if (valid && l8 == 0) {
+            double xmid = rx + (double)offset, ymid = ry;
+            if (ymid > 1.) ymid = 1. / ymid;
+            P.refined[e] = make_double2(P.fs / xmid, ymid);
+        }
+    }
+}
+
 // K8: append the unvoiced candidate, NaN check, stable sort by strength descending (periodic.rs:452-453)
 __global__ void __launch_bounds__(128) pitch_finalize_kernel(const PitchParams P, void* cand_out, int max_cand, int32_t* n_cand_out,
                                                              uint8_t* status_out, int out_f64) {
@@ -533,6 +701,8 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     P.counter = (unsigned long long*)ptr;
     VBX_REQUIRE(ctx, (int64_t)slab * cap < 0x7fffffffLL, "pitch slab too large");
 
+    const char* rv = getenv("VBX_PITCH_REFINE");
+    const bool refine_v0 = rv && rv[0] == 'v' && rv[1] == '0';  // the first (warp per candidate) version, kept for A/B runs
     for (int64_t f0 = 0; f0 < fr->n_frames; f0 += slab) {
         P.frame0 = f0;
         P.n_frames = (fr->n_frames - f0 < slab) ? fr->n_frames - f0 : slab;
@@ -541,7 +711,11 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
         pitch_lag_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
         VBX_CHECK_LAUNCH(ctx, "pitch_lag_kernel");
-        pitch_refine_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P);
+        if (refine_v0) {
+            pitch_refine_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P);
+        } else {
+            pitch_refine8_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
+        }
         VBX_CHECK_LAUNCH(ctx, "pitch_refine_kernel");
         pitch_finalize_kernel<<<(unsigned)((P.n_frames + 3) / 4), 128, 0, ctx->stream>>>(P, cand_out, max_cand, n_cand_out,
                                                                                         status_out, out_dtype == VBX_F64);
