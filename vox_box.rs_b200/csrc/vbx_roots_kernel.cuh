@@ -10,18 +10,16 @@ namespace vbx_roots {
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
 // spectrum.rs:166-192 from_root (fp64).  Returns true and fills (f, bw) if the root yields a resonance.
-__device__ __forceinline__ bool from_root_f64(double re, double im, double fs, bool strict_im, double* f_out, double* bw_out) {
+static __device__ __noinline__ bool from_root_f64(double re, double im, double fs, bool strict_im, double* f_out, double* bw_out) {
     const double freq_mul = fs / (kPi * 2.0);
     if (strict_im ? !(im > 0.0) : !(im >= 0.0)) return false;
-    double r = hypot(re, im), theta = atan2(im, re);
-    if (r > 1.0) {  // reflect around the unit circle: 1/conj(z)
-        const double ns = re * re + im * im;
-        const double ire = re / ns, iim = im / ns;  // inv(conj(z)) = conj(conj z)/|z|² = z/|z|²
-        r = hypot(ire, iim);
-        theta = atan2(iim, ire);
-    }
+    // (r, θ) = polar(z); a root outside the unit circle is reflected to 1/conj(z) = z/|z|²: same θ, radius 1/r.
+    // bw = −2·freq_mul·ln r' with r' = min(r, 1/r)  ⇒  bw = freq_mul·|ln |z|²|.  (The reference converts the
+    // reflected root to polar form again; θ and ln r agree with it to an ulp.)
+    const double theta = atan2(im, re);
+    const double ns = re * re + im * im;
     const double f = freq_mul * theta;
-    const double bw = -2.0 * freq_mul * log(r);
+    const double bw = freq_mul * fabs(log(ns));
     if (f > 50.0 && f < fs * 0.5 - 50.0) {
         *f_out = f;
         *bw_out = bw;
@@ -110,15 +108,39 @@ __global__ void __launch_bounds__(128) lpc_roots_kernel(const RootsParams Q) {
     } else {
         roots[0] = cdiv(cneg(c[0]), c[1]);  // polynomial.rs:141-144 linear tail
     }
-    // resonances: fp64 polish of the roots that can become resonances, then from_root
-    double rf[P], rb[P];
-    int cnt = 0;
+    // resonances: fp64 polish of the roots that can become resonances, then from_root.  The candidates are
+    // compacted first and handled by a real loop (one copy of the polish + atan2/log code, every lane busy):
+    // unrolling this per root made the kernel 250 KB of SASS and instruction-cache bound at scale
+    // (profiles/r1_roots_v0_icache.txt: stall_no_inst 82 %).
+    vcx<double> cz[P];
+    int cidx[P];
+    int nc = 0;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-        vcx<double> z = cmk<double>((double)roots[k].re, (double)roots[k].im);
+        const vcx<double> z = cmk<double>((double)roots[k].re, (double)roots[k].im);
         const bool cand = Q.strict_im ? (z.im > 0.0) : (z.im >= 0.0);
-        if (cand && Q.polish_steps > 0 && FAST) z = newton_polish<P>(a, z, Q.polish_steps);
+        if (cand) {
+            cz[nc] = z;
+            cidx[nc] = k;
+            ++nc;
+        } else if (Q.roots_out) {
+            if (Q.out_f64) {
+                double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+                o[0] = z.re; o[1] = z.im;
+            } else {
+                float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+                o[0] = (float)z.re; o[1] = (float)z.im;
+            }
+        }
+    }
+    double rf[P], rb[P];
+    int cnt = 0;
+#pragma unroll 1
+    for (int j = 0; j < nc; ++j) {
+        vcx<double> z = cz[j];
+        if (Q.polish_steps > 0 && FAST) z = newton_polish<P>(a, z, Q.polish_steps);
         if (Q.roots_out) {
+            const int k = cidx[j];
             if (Q.out_f64) {
                 double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
                 o[0] = z.re; o[1] = z.im;
@@ -128,29 +150,197 @@ __global__ void __launch_bounds__(128) lpc_roots_kernel(const RootsParams Q) {
             }
         }
         double fr_, bw_;
-        const bool ok = cand && from_root_f64(z.re, z.im, Q.fs, Q.strict_im != 0, &fr_, &bw_);
-        rf[k] = ok ? fr_ : -1.0;  // −1 marks "no resonance"
-        rb[k] = ok ? bw_ : 0.0;
-        cnt += ok ? 1 : 0;
+        if (from_root_f64(z.re, z.im, Q.fs, Q.strict_im != 0, &fr_, &bw_)) {
+            rf[cnt] = fr_;
+            rb[cnt] = bw_;
+            ++cnt;
+        }
     }
     if (Q.status_out) Q.status_out[f] = VBX_OK;  // NaN/inf roots yield no resonance, silently, as in the reference
     if (Q.nres_out) Q.nres_out[f] = cnt;
     if (Q.res_out) {
         // stable rank sort by frequency (lib.rs:105-110 / spectrum.rs:207), zero padding behind
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            if (rf[k] >= 0.0) {
-                int rank = 0;
-#pragma unroll
-                for (int j = 0; j < P; ++j)
-                    rank += (rf[j] >= 0.0 && (rf[j] < rf[k] || (rf[j] == rf[k] && j < k))) ? 1 : 0;
-                if (rank < R) write_res(rank, rf[k], rb[k]);
-            }
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const double fk = rf[k];
+            int rank = 0;
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) rank += (rf[j] < fk || (rf[j] == fk && j < k)) ? 1 : 0;
+            if (rank < R) write_res(rank, fk, rb[k]);
         }
         for (int s = cnt; s < R; ++s) write_res(s, 0.0, 0.0);
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Compact variant: runtime loops over the degree, coefficients in shared memory (column layout
+// [k][thread], conflict free), one copy of the Laguerre body.  ~1/10 of the SASS of the statically
+// unrolled kernel above, which is instruction-cache bound once the grid is many waves deep.
+// Same arithmetic in the same order (Horner from the deflated degree M, n = P in the formulas).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRootsThreads = 128;
+
+template <typename TR>
+__global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const RootsParams Q, const int P) {
+    extern __shared__ __align__(16) unsigned char roots_smem[];
+    constexpr int T = kRootsThreads;
+    double* a_s = reinterpret_cast<double*>(roots_smem);                    // [P+1][T] original real coefficients
+    vcx<TR>* c_s = reinterpret_cast<vcx<TR>*>(a_s + (size_t)(P + 1) * T);   // [P+1][T] working polynomial
+    vcx<TR>* r_s = c_s + (size_t)(P + 1) * T;                               // [P][T]   roots in find_roots order
+    const int tid = threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.x * T + tid;
+    if (f >= Q.n_frames) return;
+    const int R = Q.R;
+    auto write_res = [&](int slot, double fr_, double bw_) {
+        if (Q.out_f64) {
+            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            o[0] = fr_; o[1] = bw_;
+        } else {
+            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            o[0] = (float)fr_; o[1] = (float)bw_;
+        }
+    };
+    auto write_root = [&](int k, vcx<double> z) {
+        if (Q.out_f64) {
+            double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+            o[0] = z.re; o[1] = z.im;
+        } else {
+            float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+            o[0] = (float)z.re; o[1] = (float)z.im;
+        }
+    };
+    if (Q.status_in && Q.status_in[f] != VBX_OK) {  // the LPC stage failed: find_formants returns Err before root finding
+        if (Q.status_out) Q.status_out[f] = Q.status_in[f];
+        if (Q.nres_out) Q.nres_out[f] = 0;
+        if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
+        return;
+    }
+    // polynomial in ascending powers: a[k] = coefficient of z^k = lpc_{P-k}, a[P] = 1   (lib.rs:78-91)
+    auto lpc_at = [&](int idx) -> double {
+        return Q.lpc_f64 ? reinterpret_cast<const double*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx]
+                         : (double)reinterpret_cast<const float*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx];
+    };
+    for (int k = 0; k <= P; ++k) {
+        const double v = (k < P) ? lpc_at((P - k) - (Q.lpc_has_one ? 0 : 1)) : (Q.lpc_has_one ? lpc_at(0) : 1.0);
+        a_s[k * T + tid] = v;
+        c_s[k * T + tid] = cmk<TR>((TR)v, (TR)0);
+    }
+    constexpr bool FAST = (sizeof(TR) == 4);
+    const TR nn = (TR)((P - 1) * P), nref = (TR)P;
+    // polynomial.rs:116-128: for m = P down to 3: z = laguerre(coeffs, −2−2i); deflate
+#pragma unroll 1
+    for (int M = P; M >= 3; --M) {
+        vcx<TR> z = cmk<TR>((TR)-2, (TR)-2);
+#pragma unroll 1
+        for (int it = 0; it < 20; ++it) {
+            vcx<TR> a0 = c_s[M * T + tid], a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
+#pragma unroll 4
+            for (int j = M - 1; j >= 0; --j) {
+                const vcx<TR> cj = c_s[j * T + tid];
+                a2 = cfma(a2, z, a1);
+                a1 = cfma(a1, z, a0);
+                a0 = cfma(a0, z, cj);
+            }
+            if (cnorm(a0) <= (TR)1.0e-16) break;
+            const vcx<TR> ca = cdiv(cneg(a1), a0);
+            const vcx<TR> ca2 = cmul(ca, ca);
+            const vcx<TR> t2 = cdiv(cmk<TR>((TR)2 * a2.re, (TR)2 * a2.im), a0);
+            const vcx<TR> cb = csub(ca2, t2);
+            const vcx<TR> c1 = csqrt_principal(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
+            const vcx<TR> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
+            const vcx<TR> den = (cnorm(cc1) > cnorm(cc2)) ? cc1 : cc2;
+            const vcx<TR> step = cdiv(cmk<TR>(nref, (TR)0), den);
+            z = cadd(z, step);
+            if (FAST) {  // converged for the purpose of the fp64 polish that follows
+                const TR eps = (TR)3.0e-7;
+                if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) break;
+            }
+        }
+        r_s[(P - M) * T + tid] = z;
+        // deflation by the root (polynomial.rs:155-195 with other = −z)
+        vcx<TR> carry = c_s[M * T + tid];
+        c_s[M * T + tid] = cmk<TR>((TR)0, (TR)0);
+#pragma unroll 4
+        for (int i = M - 1; i >= 0; --i) {
+            const vcx<TR> old = c_s[i * T + tid];
+            c_s[i * T + tid] = carry;
+            carry = cmk<TR>(old.re + (carry.re * z.re - carry.im * z.im), old.im + (carry.re * z.im + carry.im * z.re));
+        }
+    }
+    if (P >= 2) {
+        // polynomial.rs:131-139 quadratic tail: (−c1 ± sqrt(c1² − 4 c2 c0)) / 2c2, "+" first
+        const vcx<TR> q0 = c_s[tid], q1 = c_s[T + tid], q2 = c_s[2 * T + tid];
+        const vcx<TR> a2 = cadd(q2, q2);
+        const vcx<TR> four_ac = cmul(cmul(cmk<TR>((TR)4, (TR)0), q2), q0);
+        const vcx<TR> d = csqrt_principal(csub(cmul(q1, q1), four_ac));
+        const vcx<TR> x = cneg(q1);
+        r_s[(P - 2) * T + tid] = cdiv(cadd(x, d), a2);
+        r_s[(P - 1) * T + tid] = cdiv(csub(x, d), a2);
+    } else {
+        r_s[tid] = cdiv(cneg(c_s[tid]), c_s[T + tid]);  // polynomial.rs:141-144 linear tail
+    }
+    // resonances: fp64 polish of the roots that can become resonances (two Newton steps on the ORIGINAL
+    // polynomial), then from_root; the sorted resonances are staged in the (now free) working-polynomial columns
+    // sorted-resonance staging in the thread's OWN column of the (now free) working polynomial: for fp64 a
+    // (frequency, bandwidth) pair is one 16-byte element of c_s; for fp32 an element is 8 bytes = one double,
+    // so frequencies go to rows 0..P−1 and bandwidths to rows P..2P−1 (row P+cnt is r_s row cnt−1 < k, already
+    // consumed).  Any other mapping lands in another thread's column while that thread may still be solving.
+    double* rf = reinterpret_cast<double*>(c_s);
+    auto stage_put = [&](int i, double fr_, double bw_) {
+        if (sizeof(TR) == 8) { rf[(i * T + tid) * 2] = fr_; rf[(i * T + tid) * 2 + 1] = bw_; }
+        else { rf[i * T + tid] = fr_; rf[(P + i) * T + tid] = bw_; }
+    };
+    auto stage_f = [&](int i) -> double { return sizeof(TR) == 8 ? rf[(i * T + tid) * 2] : rf[i * T + tid]; };
+    auto stage_b = [&](int i) -> double { return sizeof(TR) == 8 ? rf[(i * T + tid) * 2 + 1] : rf[(P + i) * T + tid]; };
+    int cnt = 0;
+#pragma unroll 1
+    for (int k = 0; k < P; ++k) {
+        const vcx<TR> zr = r_s[k * T + tid];
+        vcx<double> z = cmk<double>((double)zr.re, (double)zr.im);
+        const bool cand = Q.strict_im ? (z.im > 0.0) : (z.im >= 0.0);
+        if (cand && FAST && Q.polish_steps > 0) {
+            for (int s = 0; s < Q.polish_steps; ++s) {
+                vcx<double> p0 = cmk<double>(a_s[P * T + tid], 0.0), p1 = cmk<double>(0.0, 0.0);
+#pragma unroll 4
+                for (int j = P - 1; j >= 0; --j) {
+                    p1 = cfma(p1, z, p0);
+                    p0 = cmk<double>(fma(p0.re, z.re, fma(-p0.im, z.im, a_s[j * T + tid])), fma(p0.re, z.im, p0.im * z.re));
+                }
+                if (cnorm_sqr(p1) == 0.0) break;
+                z = csub(z, cdiv(p0, p1));
+            }
+        }
+        if (Q.roots_out) write_root(k, z);
+        double fr_, bw_;
+        if (cand && from_root_f64(z.re, z.im, Q.fs, Q.strict_im != 0, &fr_, &bw_)) {
+            stage_put(cnt, fr_, bw_);
+            ++cnt;
+        }
+    }
+    if (Q.status_out) Q.status_out[f] = VBX_OK;  // NaN/inf roots yield no resonance, silently, as in the reference
+    if (Q.nres_out) Q.nres_out[f] = cnt;
+    if (Q.res_out) {
+        // stable rank sort by frequency (lib.rs:105-110 / spectrum.rs:207), zero padding behind
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const double fk = stage_f(k);
+            int rank = 0;
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                const double fj = stage_f(j);
+                rank += (fj < fk || (fj == fk && j < k)) ? 1 : 0;
+            }
+            if (rank < R) write_res(rank, fk, stage_b(k));
+        }
+        for (int s = cnt; s < R; ++s) write_res(s, 0.0, 0.0);
+    }
+}
+
+static inline size_t roots_rt_smem_bytes(int P, bool f32) {
+    const size_t cs = f32 ? 8 : 16;
+    return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)(P + 1) * cs + (size_t)P * cs);
+}
 
 typedef void (*roots_kernel_t)(const RootsParams);
 constexpr int kMaxRootsOrder = 24;
