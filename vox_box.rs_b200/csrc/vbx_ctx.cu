@@ -41,6 +41,21 @@ int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes) {
     return VBX_OK;
 }
 
+int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pipe_bytes) return VBX_OK;
+    VBX_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->pipe) cudaFree(ctx->pipe);
+    ctx->pipe = nullptr;
+    ctx->pipe_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->pipe, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return vbx_fail(ctx, VBX_ERR_NOMEM, "host pipeline block: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->pipe_bytes = bytes;
+    return VBX_OK;
+}
+
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->pinned_bytes) return VBX_OK;
     VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -200,10 +215,17 @@ int vbx_ctx_create(int device, vbx_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
         delete ctx;
         return VBX_ERR_CUDA;
     }
+    for (int i = 0; i < 6; ++i)
+        if (cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return VBX_ERR_CUDA;
+        }
     *out = ctx;
     return VBX_OK;
 }
@@ -211,11 +233,15 @@ int vbx_ctx_create(int device, vbx_ctx** out) {
 int vbx_ctx_destroy(vbx_ctx* ctx) {
     if (!ctx) return VBX_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for (auto& kv : ctx->windows) cudaFree(kv.second);
     vbx_mfcc_cache_free(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pipe) cudaFree(ctx->pipe);
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev_pipe[i]);
+    cudaStreamDestroy(ctx->s_h2d);
+    cudaStreamDestroy(ctx->s_d2h);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaStreamDestroy(ctx->stream);

@@ -18,6 +18,7 @@
 
 #include "vbx_complex.cuh"
 #include "vbx_internal.cuh"
+#include "vbx_pipeline.cuh"
 #include "vbx_roots_kernel.cuh"
 
 namespace {
@@ -807,7 +808,8 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
 
 }  // extern "C"
 
-// host twin of vbx_find_formants: H2D the audio extent + starting estimates, run, D2H everything requested
+// host twin of vbx_find_formants: chunked H2D / kernels / D2H pipeline over whole utterances (vbx_pipeline.cuh);
+// the tracker state travels once (in before the first chunk, out after the last)
 extern "C" int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
                                       int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
                                       void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
@@ -820,45 +822,35 @@ extern "C" int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, do
     cudaSetDevice(ctx->device);
     const size_t pair = (dtype == VBX_F64) ? 16 : 8;
     const int64_t J = vbx_frames_per_segment(frames), segs = F / J;
-    const size_t in_bytes = (size_t)vbx_frames_extent(frames) * vbx_dtype_size(frames->dtype);
     const size_t est_bytes = (est_inout && n_formants > 0) ? (size_t)segs * n_formants * pair : 0;
-    const size_t trk_bytes = (tracks_out && n_formants > 0) ? (size_t)F * n_formants * pair : 0;
-    const size_t res_bytes = resonances_out ? (size_t)F * VBX_MAX_RESONANCES * pair : 0;
-    const size_t nres_bytes = nres_out ? (size_t)F * 4 : 0;
-    const size_t st_bytes = status_out ? (size_t)F : 0;
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    // a private device block (the pipeline itself uses the context arena)
-    void* blk = nullptr;
-    const size_t total = al(in_bytes) + al(est_bytes) + al(trk_bytes) + al(res_bytes) + al(nres_bytes) + al(st_bytes);
-    cudaError_t e = cudaMalloc(&blk, total);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return vbx_fail(ctx, VBX_ERR_NOMEM, "find_formants_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+    void* d_est = nullptr;
+    if (est_bytes) {
+        cudaError_t e = cudaMalloc(&d_est, est_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return vbx_fail(ctx, VBX_ERR_NOMEM, "find_formants_host: cudaMalloc(%zu) failed: %s", est_bytes, cudaGetErrorString(e));
+        }
     }
-    char* p = (char*)blk;
-    void* d_in = p; p += al(in_bytes);
-    void* d_est = est_bytes ? p : nullptr; p += al(est_bytes);
-    void* d_trk = trk_bytes ? p : nullptr; p += al(trk_bytes);
-    void* d_res = res_bytes ? p : nullptr; p += al(res_bytes);
-    int32_t* d_nres = nres_bytes ? (int32_t*)p : nullptr; p += al(nres_bytes);
-    uint8_t* d_st = st_bytes ? (uint8_t*)p : nullptr;
     auto run = [&]() -> int {
-        VBX_CUDA(ctx, cudaMemcpyAsync(d_in, frames->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
         if (est_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(d_est, est_inout, est_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        vbx_frames dfr = *frames;
-        dfr.base = d_in;
-        int s = vbx_find_formants(ctx, &dfr, sample_rate, n_coeffs, lpc_method, d_est, n_formants, d_trk, d_res, d_nres, d_st, dtype);
+        vbx_host_out outs[4] = {{n_formants > 0 ? tracks_out : nullptr, (size_t)n_formants * pair, nullptr},
+                                {resonances_out, (size_t)VBX_MAX_RESONANCES * pair, nullptr},
+                                {nres_out, 4, nullptr},
+                                {status_out, 1, nullptr}};
+        int s = vbx_run_chunked(ctx, frames, outs, 4, [&](const vbx_frames* dfr, int64_t, int64_t seg0, vbx_host_out* o) -> int {
+            void* est = d_est ? (char*)d_est + (size_t)seg0 * n_formants * pair : nullptr;
+            return vbx_find_formants(ctx, dfr, sample_rate, n_coeffs, lpc_method, est, n_formants, o[0].dev, o[1].dev,
+                                     (int32_t*)o[2].dev, (uint8_t*)o[3].dev, dtype);
+        }, /*max_chunks=*/4);  // the tracker is sequential inside an utterance: a launch costs ~3 ms however few utterances it gets
         if (s != VBX_OK) return s;
-        if (est_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(est_inout, d_est, est_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (trk_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(tracks_out, d_trk, trk_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (res_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(resonances_out, d_res, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (nres_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(nres_out, d_nres, nres_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (st_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(status_out, d_st, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (est_bytes) {
+            VBX_CUDA(ctx, cudaMemcpyAsync(est_inout, d_est, est_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         return VBX_OK;
     };
     st = run();
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(blk);
+    if (d_est) cudaFree(d_est);
     return st;
 }

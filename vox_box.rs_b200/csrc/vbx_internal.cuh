@@ -31,6 +31,11 @@ struct vbx_ctx {
     size_t arena_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // host-call pipeline (vbx_pipeline.cuh): copy-in / copy-out streams, events, double-buffered device block
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* pipe = nullptr;
+    size_t pipe_bytes = 0;
     // window tables (device, f64), keyed by (kind << 32 | n)
     std::map<uint64_t, double*> windows;
     vbx_mfcc_cache* mfcc_cache = nullptr;
@@ -40,6 +45,7 @@ struct vbx_ctx {
 int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
+int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes);          // ensures ctx->pipe has >= bytes
 int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out);  // cached device table (ones for NONE)
 void vbx_window_fill_host(int kind, int n, double* out);
 

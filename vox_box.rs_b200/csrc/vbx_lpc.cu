@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "vbx_internal.cuh"
+#include "vbx_pipeline.cuh"
 
 namespace {
 
@@ -505,7 +506,7 @@ int lpc_dispatch(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, vo
     return launch_lpc<float>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
 }
 
-// host twin: H2D the contiguous extent, run, D2H the outputs
+// host twin: chunked H2D / kernels / D2H pipeline (vbx_pipeline.cuh)
 int lpc_host(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* ac_out, void* kc_out, int out_dtype,
              bool do_levinson) {
     if (!ctx) return VBX_ERR_BADARG;
@@ -514,32 +515,13 @@ int lpc_host(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* 
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     if (fr->n_frames == 0) return VBX_OK;
     cudaSetDevice(ctx->device);
-    const size_t es = vbx_dtype_size(fr->dtype), os = vbx_dtype_size(out_dtype);
-    const size_t in_bytes = (size_t)vbx_frames_extent(fr) * es;
-    const size_t F = (size_t)fr->n_frames;
-    const size_t r_bytes = r_out ? F * n_lags * os : 0;
-    const size_t ac_bytes = (do_levinson && ac_out) ? F * n_lags * os : 0;
-    const size_t kc_bytes = (do_levinson && kc_out) ? F * (n_lags - 1) * os : 0;
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    // the fallback path may also use the arena for a scratch r: keep our block after that region
-    const size_t scratch = al(F * n_lags * sizeof(double));
-    st = vbx_arena_reserve(ctx, scratch + al(in_bytes) + al(r_bytes) + al(ac_bytes) + al(kc_bytes));
-    if (st != VBX_OK) return st;
-    char* p = (char*)ctx->arena + scratch;
-    void* d_in = p; p += al(in_bytes);
-    void* d_r = r_bytes ? p : nullptr; p += al(r_bytes);
-    void* d_ac = ac_bytes ? p : nullptr; p += al(ac_bytes);
-    void* d_kc = kc_bytes ? p : nullptr;
-    VBX_CUDA(ctx, cudaMemcpyAsync(d_in, fr->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    vbx_frames dfr = *fr;
-    dfr.base = d_in;
-    st = lpc_dispatch(ctx, &dfr, n_lags, d_r, d_ac, d_kc, out_dtype, do_levinson);
-    if (st != VBX_OK) return st;
-    if (r_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(r_out, d_r, r_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ac_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(ac_out, d_ac, ac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (kc_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(kc_out, d_kc, kc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VBX_OK;
+    const size_t os = vbx_dtype_size(out_dtype);
+    vbx_host_out outs[3] = {{r_out, (size_t)n_lags * os, nullptr},
+                            {do_levinson ? ac_out : nullptr, (size_t)n_lags * os, nullptr},
+                            {do_levinson ? kc_out : nullptr, (size_t)(n_lags - 1) * os, nullptr}};
+    return vbx_run_chunked(ctx, fr, outs, 3, [&](const vbx_frames* dfr, int64_t, int64_t, vbx_host_out* o) -> int {
+        return lpc_dispatch(ctx, dfr, n_lags, o[0].dev, o[1].dev, o[2].dev, out_dtype, do_levinson);
+    });
 }
 
 }  // namespace

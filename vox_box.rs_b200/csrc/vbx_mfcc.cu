@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "vbx_internal.cuh"
+#include "vbx_pipeline.cuh"
 
 namespace {
 
@@ -460,24 +461,13 @@ int vbx_mfcc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t num_coeffs, in
     if (!ctx) return VBX_ERR_BADARG;
     int st = mfcc_check(ctx, frames, num_coeffs, n_keep, sample_rate, out, out_dtype);
     if (st != VBX_OK) return st;
-    const int64_t F = frames->n_frames;
-    if (F == 0) return VBX_OK;
+    if (frames->n_frames == 0) return VBX_OK;
     cudaSetDevice(ctx->device);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t in_bytes = (size_t)vbx_frames_extent(frames) * vbx_dtype_size(frames->dtype);
-    const size_t out_bytes = (size_t)F * n_keep * vbx_dtype_size(out_dtype);
-    st = vbx_arena_reserve(ctx, al(in_bytes) + al(out_bytes));
-    if (st != VBX_OK) return st;
-    void* d_in = ctx->arena;
-    void* d_out = (char*)ctx->arena + al(in_bytes);
-    VBX_CUDA(ctx, cudaMemcpyAsync(d_in, frames->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    vbx_frames dfr = *frames;
-    dfr.base = d_in;
-    st = vbx_mfcc(ctx, &dfr, num_coeffs, n_keep, freq_lo, freq_hi, sample_rate, d_out, nullptr, out_dtype);
-    if (st != VBX_OK) return st;
-    VBX_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VBX_OK;
+    vbx_host_out outs[1] = {{out, (size_t)n_keep * vbx_dtype_size(out_dtype), nullptr}};
+    // chunked H2D / kernels / D2H pipeline (vbx_pipeline.cuh)
+    return vbx_run_chunked(ctx, frames, outs, 1, [&](const vbx_frames* dfr, int64_t, int64_t, vbx_host_out* o) -> int {
+        return vbx_mfcc(ctx, dfr, num_coeffs, n_keep, freq_lo, freq_hi, sample_rate, o[0].dev, nullptr, out_dtype);
+    });
 }
 
 int vbx_dct(vbx_ctx* ctx, const void* signal, int32_t dtype, int64_t n_signals, int32_t n, void* coeffs) {

@@ -27,6 +27,7 @@
 #include <cmath>
 
 #include "vbx_internal.cuh"
+#include "vbx_pipeline.cuh"
 
 namespace {
 
@@ -758,42 +759,15 @@ int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, d
     if (!ctx) return VBX_ERR_BADARG;
     int st = pitch_check(ctx, frames, max_candidates, cand_out, out_dtype);
     if (st != VBX_OK) return st;
-    const int64_t F = frames->n_frames;
-    if (F == 0) return VBX_OK;
+    if (frames->n_frames == 0) return VBX_OK;
     cudaSetDevice(ctx->device);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t pair = (out_dtype == VBX_F64) ? 16 : 8;
-    const size_t in_bytes = (size_t)vbx_frames_extent(frames) * vbx_dtype_size(frames->dtype);
-    const size_t cand_bytes = (size_t)F * max_candidates * pair;
-    const size_t n_bytes = n_cand_out ? (size_t)F * 4 : 0, st_bytes = status_out ? (size_t)F : 0;
-    void* blk = nullptr;  // private block: the kernels use the context arena
-    const size_t total = al(in_bytes) + al(cand_bytes) + al(n_bytes) + al(st_bytes);
-    cudaError_t e = cudaMalloc(&blk, total);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return vbx_fail(ctx, VBX_ERR_NOMEM, "pitch_host: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
-    }
-    char* p = (char*)blk;
-    void* d_in = p; p += al(in_bytes);
-    void* d_cand = p; p += al(cand_bytes);
-    int32_t* d_n = n_bytes ? (int32_t*)p : nullptr; p += al(n_bytes);
-    uint8_t* d_st = st_bytes ? (uint8_t*)p : nullptr;
-    auto run = [&]() -> int {
-        VBX_CUDA(ctx, cudaMemcpyAsync(d_in, frames->base, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        vbx_frames dfr = *frames;
-        dfr.base = d_in;
-        int s = vbx_pitch(ctx, &dfr, sample_rate, threshold, min_hz, max_hz, max_candidates, d_cand, d_n, d_st, out_dtype);
-        if (s != VBX_OK) return s;
-        VBX_CUDA(ctx, cudaMemcpyAsync(cand_out, d_cand, cand_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (n_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(n_cand_out, d_n, n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (st_bytes) VBX_CUDA(ctx, cudaMemcpyAsync(status_out, d_st, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return VBX_OK;
-    };
-    st = run();
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(blk);
-    return st;
+    vbx_host_out outs[3] = {{cand_out, (size_t)max_candidates * pair, nullptr}, {n_cand_out, 4, nullptr}, {status_out, 1, nullptr}};
+    // chunked H2D / kernels / D2H pipeline (vbx_pipeline.cuh); output rows are indexed from the chunk's first frame
+    return vbx_run_chunked(ctx, frames, outs, 3, [&](const vbx_frames* dfr, int64_t, int64_t, vbx_host_out* o) -> int {
+        return vbx_pitch(ctx, dfr, sample_rate, threshold, min_hz, max_hz, max_candidates, o[0].dev, (int32_t*)o[1].dev,
+                         (uint8_t*)o[2].dev, out_dtype);
+    });
 }
 
 int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_frames, int32_t max_candidates, void* out) {
