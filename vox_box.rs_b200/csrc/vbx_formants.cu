@@ -597,6 +597,201 @@ __global__ void __launch_bounds__(128) tracker_kernel(const TrackParams T) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// McCandless tracker for the fused find_formants path, one THREAD per utterance, slots held as INDICES.
+//
+// The warp-per-utterance kernel above spends ~1100 warp instructions per frame step (warp-wide arg-min
+// butterflies, every lane repeating the serial slot logic on (frequency, bandwidth) pairs), so a launch
+// costs ~3 ms however few utterances it gets and ~30 % of the C3 step at scale.  In the fused path the
+// frame's resonances are known to be: `nres` distinct entries sorted by ascending frequency (all > 50 Hz),
+// followed by zero padding up to 32 (lib.rs:94-114).  That lets a slot be a small integer:
+//   −1 = None, i in [0, nres) = resonance i, nres = "the (0, 0) pad" (all pads are the same value; only the
+//   first can win the strict `<` of step 2),
+// and turns the step into integer logic: equality of slots = equality of indices; the two distances step 3
+// compares are the step-2 minima bd[r], bd[w] (both slots hold the same resonance); the sort by frequency
+// is a sort of the keys (None < pad < index order) through a 12-comparator network; only the ≤ 6 winners'
+// values are fetched.  Rows are streamed through shared memory with cp.async one frame ahead (16-byte
+// chunks, [chunk][thread] layout), nres/status are prefetched one frame ahead, and a warp advances 32
+// utterances per instruction.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrkThreads = 64;
+
+template <bool RES_F64>
+__global__ void __launch_bounds__(kTrkThreads) tracker_idx_kernel(const TrackParams T, const int chunks_per_row) {
+    extern __shared__ __align__(16) unsigned char trk_smem[];
+    constexpr int NS = VBX_MAX_FORMANT_SLOTS;
+    constexpr int TT = kTrkThreads;
+    constexpr int NONE = -1;
+    const int tid = threadIdx.x;
+    const int64_t u = (int64_t)blockIdx.x * TT + tid;
+    if (u >= T.n_segments) return;
+    const int n_est = T.n_est, n6 = n_est < NS ? n_est : NS;
+    const int R = T.R;
+    const int n_stored = R < T.n_res_eff ? R : T.n_res_eff;
+    const size_t row_bytes = (size_t)R * (RES_F64 ? 16 : 8);
+    uint4* buf = reinterpret_cast<uint4*>(trk_smem);  // [2][chunks_per_row][TT] 16-byte chunks
+    const char* res_base = reinterpret_cast<const char*>(T.res) + (size_t)u * T.seg_frames * row_bytes;
+    auto issue = [&](int64_t j, int b) {
+        const char* src = res_base + (size_t)j * row_bytes;
+        for (int c = 0; c < chunks_per_row; ++c) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + ((size_t)b * chunks_per_row + c) * TT + tid);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)c * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto entry = [&](int b, int i, double& f, double& bw) {  // stored entry i of the staged row b
+        if (RES_F64) {
+            const double2 v = *reinterpret_cast<const double2*>(buf + ((size_t)b * chunks_per_row + i) * TT + tid);
+            f = v.x; bw = v.y;
+        } else {
+            const float2 v = *(reinterpret_cast<const float2*>(buf + ((size_t)b * chunks_per_row + (i >> 1)) * TT + tid) + (i & 1));
+            f = (double)v.x; bw = (double)v.y;
+        }
+    };
+    double ef[NS], eb[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        ef[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2) : 0.0;
+        eb[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2 + 1) : 0.0;
+    }
+    const int64_t f0 = u * T.seg_frames;
+    int st_next = 0, nres_next = 0;
+    if (T.seg_frames > 0) {
+        issue(0, 0);
+        st_next = T.status ? (int)T.status[f0] : 0;
+        nres_next = T.nres[f0];
+    }
+    for (int64_t j = 0; j < T.seg_frames; ++j) {
+        const int64_t f = f0 + j;
+        const int b = (int)(j & 1);
+        const int st = st_next, nres_f = nres_next;
+        if (j + 1 < T.seg_frames) {
+            issue(j + 1, b ^ 1);
+            st_next = T.status ? (int)T.status[f + 1] : 0;
+            nres_next = T.nres[f + 1];
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        if (st == VBX_OK) {
+            const int n_real = nres_f < n_stored ? nres_f : n_stored;
+            const bool has_pad = n_real < T.n_res_eff;
+            const int pad = n_real;  // canonical index of the (0, 0) padding
+            // step 2: nearest resonance per estimate (fold from entry 0, replace on strict `<`, NaN never wins)
+            double bd[NS];
+            int slot[NS];
+            {
+                double f_, b_;
+                if (n_real > 0) entry(b, 0, f_, b_); else f_ = 0.0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) { bd[k] = fabs(f_ - ef[k]); slot[k] = 0; }
+            }
+            for (int i = 1; i < n_real; ++i) {
+                double f_, b_;
+                entry(b, i, f_, b_);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const double d = fabs(f_ - ef[k]);
+                    if (d < bd[k]) { bd[k] = d; slot[k] = i; }
+                }
+            }
+            if (has_pad && n_real > 0) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const double d = fabs(0.0 - ef[k]);
+                    if (d < bd[k]) { bd[k] = d; slot[k] = pad; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (k >= n6) slot[k] = NONE;
+            // step 3: remove duplicates; w = last kept slot (a Some slot whenever it is consulted)
+            int w = 0, wv = slot[0];
+            double wbd = bd[0];
+            bool has_unassigned = false;
+#pragma unroll
+            for (int r = 1; r < NS; ++r) {
+                if (slot[r] != NONE) {
+                    if (wv != NONE && slot[r] == wv) {
+                        has_unassigned = true;
+                        if (bd[r] < wbd) {
+#pragma unroll
+                            for (int q = 0; q < NS; ++q)
+                                if (q == w) slot[q] = NONE;
+                            w = r; wbd = bd[r];  // wv unchanged (same resonance)
+                        } else {
+                            slot[r] = NONE;
+                        }
+                    } else {
+                        w = r; wv = slot[r]; wbd = bd[r];
+                    }
+                }
+            }
+            // step 4: unassigned peaks; the resonance index doubles as the slot index, so only indices < 6 can act
+            if (has_unassigned) {
+#pragma unroll
+                for (int jj = 0; jj < NS; ++jj) {
+                    if (jj < T.n_res_eff) {
+                        const int c = jj < n_real ? jj : pad;
+                        bool contained = false;
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) contained = contained || (slot[q] == c);
+                        if (!contained) {
+                            if (slot[jj] == NONE) {
+                                slot[jj] = c;
+                            } else if (jj > 0 && slot[jj > 0 ? jj - 1 : 0] == NONE) {
+                                slot[jj > 0 ? jj - 1 : 0] = slot[jj];
+                                slot[jj] = c;
+                            } else if (jj + 1 < NS && slot[jj + 1 < NS ? jj + 1 : NS - 1] == NONE) {
+                                slot[jj + 1 < NS ? jj + 1 : NS - 1] = slot[jj];
+                                slot[jj] = c;
+                            }
+                        }
+                    }
+                }
+            }
+            // step 5: sort — None first, then ascending frequency: pad (0 Hz) < resonance 0 < resonance 1 < …
+            int key[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) key[q] = (slot[q] == NONE) ? -1 : (slot[q] == pad ? 0 : slot[q] + 1);
+#define VBX_CE(a, b) { const int lo = min(key[a], key[b]), hi = max(key[a], key[b]); key[a] = lo; key[b] = hi; }
+            VBX_CE(0, 5) VBX_CE(1, 3) VBX_CE(2, 4) VBX_CE(1, 2) VBX_CE(3, 4) VBX_CE(0, 3) VBX_CE(2, 5) VBX_CE(0, 1) VBX_CE(2, 3)
+            VBX_CE(4, 5) VBX_CE(1, 2) VBX_CE(3, 4)
+#undef VBX_CE
+            // winners (Some, f > 0 ⇔ key > 0) overwrite the leading estimates, in order
+            int z = 0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) z += (key[q] <= 0) ? 1 : 0;
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                int kk = 0;
+#pragma unroll
+                for (int q = 0; q < NS; ++q)
+                    if (q == z + t) kk = key[q];
+                if (z + t < NS && t < n_est) entry(b, kk - 1, ef[t], eb[t]);
+            }
+        }
+        if (T.tracks_out) {
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+                if (t < n_est) {
+                    st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + t) * 2, ef[t]);
+                    st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + t) * 2 + 1, eb[t]);
+                }
+            for (int t = NS; t < n_est; ++t) {  // estimates beyond the 6 slots never change (spectrum.rs:235 zip)
+                st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + t) * 2, ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + t) * 2));
+                st_pair(T.tracks_out, T.out_f64, ((size_t)f * n_est + t) * 2 + 1, ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + t) * 2 + 1));
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NS; ++t)
+        if (t < n6) {
+            st_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + t) * 2, ef[t]);
+            st_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + t) * 2 + 1, eb[t]);
+        }
+}
+
 int root_precision_default() {
     const char* e = getenv("VBX_ROOTS_F64");
     return (e && e[0] == '1') ? 1 : 0;
@@ -725,9 +920,10 @@ int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dtype, int6
     return VBX_OK;
 }
 
-int vbx_estimate_formants(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
-                          int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
-                          int32_t n_estimates, void* tracks_out, int32_t dtype) {
+// nres (optional, internal): per-frame count of real resonances when every stored entry behind it is known to be (0, 0)
+static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
+                                  int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
+                                  int32_t n_estimates, void* tracks_out, int32_t dtype, const int32_t* nres) {
     if (!ctx) return VBX_ERR_BADARG;
     VBX_REQUIRE(ctx, res_dtype == VBX_F32 || res_dtype == VBX_F64, "res_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
@@ -739,14 +935,43 @@ int vbx_estimate_formants(vbx_ctx* ctx, const void* resonances, int32_t res_dtyp
     VBX_REQUIRE(ctx, resonances && est_inout, "resonances / est_inout is NULL");
     cudaSetDevice(ctx->device);
     TrackParams T;
-    T.res = resonances; T.nres = nullptr; T.status = status_in; T.est_inout = est_inout; T.tracks_out = tracks_out;
+    T.res = resonances; T.nres = nres; T.status = status_in; T.est_inout = est_inout; T.tracks_out = tracks_out;
     T.n_segments = n_segments; T.seg_frames = frames_per_segment; T.R = res_slots; T.n_res_eff = n_resonances;
     T.n_est = n_estimates; T.res_f64 = (res_dtype == VBX_F64); T.out_f64 = (dtype == VBX_F64);
+    // fused path (per-frame counts known, rows sorted and zero padded): the index-based thread-per-utterance kernel,
+    // when the rows can be staged with 16-byte cp.async chunks.  Arbitrary caller resonances (vbx_estimate_formants),
+    // odd fp32 row lengths, or VBX_TRACKER=warp (A/B runs): the value-based warp-per-utterance kernel.
+    const size_t pair_bytes = (res_dtype == VBX_F64) ? 16 : 8;
+    const size_t row_bytes = (size_t)res_slots * pair_bytes;
+    const char* tv = getenv("VBX_TRACKER");
+    const bool aligned = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(resonances) & 15) == 0);
+    const int chunks = (int)(row_bytes / 16);
+    const size_t smem = (size_t)2 * chunks * kTrkThreads * 16;
+    if (nres && aligned && smem <= ctx->smem_optin && !(tv && tv[0] == 'w')) {
+        const int64_t grid = (n_segments + kTrkThreads - 1) / kTrkThreads;
+        VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
+        if (res_dtype == VBX_F64) {
+            VBX_CUDA(ctx, cudaFuncSetAttribute(tracker_idx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tracker_idx_kernel<true><<<(unsigned)grid, kTrkThreads, smem, ctx->stream>>>(T, chunks);
+        } else {
+            VBX_CUDA(ctx, cudaFuncSetAttribute(tracker_idx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tracker_idx_kernel<false><<<(unsigned)grid, kTrkThreads, smem, ctx->stream>>>(T, chunks);
+        }
+        VBX_CHECK_LAUNCH(ctx, "tracker_idx_kernel");
+        return VBX_OK;
+    }
     const int64_t grid = (n_segments + 3) / 4;  // one warp per segment
     VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
     tracker_kernel<<<(unsigned)grid, 128, 0, ctx->stream>>>(T);
     VBX_CHECK_LAUNCH(ctx, "tracker_kernel");
     return VBX_OK;
+}
+
+int vbx_estimate_formants(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
+                          int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
+                          int32_t n_estimates, void* tracks_out, int32_t dtype) {
+    return estimate_formants_impl(ctx, resonances, res_dtype, res_slots, n_resonances, n_segments, frames_per_segment, status_in,
+                                  est_inout, n_estimates, tracks_out, dtype, nullptr);
 }
 
 // lib.rs:40-116 find_formants, batched: LPC (Burg on the frame as windowed by frames->window — HANN_PERIODIC
@@ -775,9 +1000,11 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     const bool own_res = (resonances_out == nullptr);
     const int R = own_res ? p : VBX_MAX_RESONANCES;
     const size_t res_bytes = own_res ? al((size_t)F * R * res_es) : 0;
-    st = vbx_arena_reserve(ctx, lpc_bytes + 2 * st_bytes + res_bytes);
+    const size_t nres_bytes = nres_out ? 0 : al((size_t)F * sizeof(int32_t));
+    st = vbx_arena_reserve(ctx, lpc_bytes + 2 * st_bytes + res_bytes + nres_bytes);
     if (st != VBX_OK) return st;
     char* base = (char*)ctx->arena;
+    int32_t* d_nres = nres_out ? nres_out : (int32_t*)(base + lpc_bytes + 2 * st_bytes + res_bytes);
     double* d_lpc = (double*)base;
     uint8_t* d_st_lpc = (uint8_t*)(base + lpc_bytes);
     uint8_t* d_st = status_out ? status_out : (uint8_t*)(base + lpc_bytes + st_bytes);
@@ -796,11 +1023,12 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     }
     if (st != VBX_OK) return st;
     st = vbx_lpc_to_resonances(ctx, d_lpc, VBX_F64, F, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
-                               d_res, R, nres_out, nullptr, d_st, dtype, -1);
+                               d_res, R, d_nres, nullptr, d_st, dtype, -1);
     if (st != VBX_OK) return st;
     if (n_formants > 0 && est_inout) {
         const int64_t J = vbx_frames_per_segment(frames);
-        st = vbx_estimate_formants(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, F / J, J, d_st, est_inout, n_formants, tracks_out, dtype);
+        st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, F / J, J, d_st, est_inout, n_formants, tracks_out, dtype,
+                                    d_nres);
         if (st != VBX_OK) return st;
     }
     return VBX_OK;
