@@ -359,36 +359,58 @@ class Workload:
             self.outputs = "13 MFCC per frame fp32"
             self._keep = (d_o,)
 
-    def roofline(self, frames_per_s, peaks, hbm_peak, hbm_src):
-        """Dominant kernel of the step against the pipe that bounds it + the HBM view."""
+    def kernel_table(self):
+        """Algorithmic work per frame of every kernel of the step (SURVEY §8d figures, split per kernel):
+        name -> (pipe that bounds it, flop per frame, HBM bytes per frame, committed ncu summary or None)."""
         cfg, N, hop = self.cfg, self.cfg["n"], self.cfg["hop"]
-        kind = cfg["kind"]
-        if kind == "lpc":
-            p = cfg["p"]
-            flop, pipe, kern, prof = 2 * (p + 1) * N + N + 350, "fp64", "lpc_fused_kernel<13,float>", "r1_lpc_fused_v1_full.txt"
-            byts = 4 * hop + 2 * 4 * (p + 1)
-        elif kind == "formants":
-            p = cfg["p"]
-            # SURVEY §8d C3 path A: lag MACs + window + Levinson (fp64) | roots 10·20·(3·12·8+60) (fp32) | resonances
-            flop, pipe, kern, prof = 2 * (p + 1) * N + N + 350, "fp64", "lpc_fused_kernel<13,float> (+ lpc_roots_kernel fp32, tracker_kernel)", None
-            byts = 4 * hop + 4 * 2 * 4
-        elif kind == "pitch":
-            # SURVEY §8d C4: 410 k flop lag sweep (fp32) + ~2.5 M flop Brent/sinc refinement (fp64), the dominant kernel
-            flop, pipe, kern, prof = 2.5e6, "fp64", "pitch_refine_kernel", "r1_refine_v0_full.txt"
-            byts = 4 * hop + 140
-        else:
-            # SURVEY §8d C5: 5·N·log2(N) complex FFT + band MACs + 40 log10 + 2·13·40 DCT ≈ 19.5 k flop
-            flop, pipe, kern, prof = 19.5e3, "fp64", "mfcc_kernel<float,double>", "r1_mfcc_v0_full.txt"
-            byts = 4 * hop + 4 * 13
-        peak = peaks[pipe + "_tflops"]
-        ach = flop * frames_per_s / 1e12
-        ach_gb = byts * frames_per_s / 1e9
-        return ({"bound": pipe, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                 "traffic": _ncu_traffic(prof) if prof else None, "kernel": kern, "flop_per_frame": flop,
-                 "peak_source": "vbx_measure_peaks: dependent-free FMA loop on this device, this run",
-                 "note": "whole-step time used for the dominant kernel (its share of the step is in profiles/)"},
-                {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
-                 "bytes_per_frame": byts, "peak_source": hbm_src})
+        p = cfg.get("p", 12)
+        lpc = ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_fused_v1_full.txt")
+        return {
+            "lpc": {"lpc_fused_kernel": lpc},
+            "formants": {
+                "lpc_fused_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), None),
+                # 10 Laguerre solves x 20 iterations x (3*12 complex FMA*8 + ~60) + polish/resonances ~ 70 k flop (fp32 pipe)
+                "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, None),
+                "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_v0_full.txt"),
+            },
+            "pitch": {
+                "pitch_lag_kernel": ("fp32", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, "r1_lag_v0_full.txt"),
+                # ~16 candidates x ~26 Brent evaluations x 2(lag+2) terms x ~30 flop (SURVEY §8d C4)
+                "pitch_refine_kernel": ("fp64", 2.5e6, 8 * N, "r1_refine_v1_full.txt"),
+                "pitch_finalize_kernel": ("fp64", 500.0, 16 * 16 + 140, None),
+            },
+            "mfcc": {"mfcc_kernel": ("fp64", 19.5e3, 4 * hop + 4 * 13, "r1_mfcc_v0_full.txt")},
+        }[cfg["kind"]]
+
+    def roofline(self, prof, steps, peaks, hbm_peak, hbm_src):
+        """Per-kernel roofline from the per-kernel device times measured over the timed region (vbx_profile_*):
+        achieved = algorithmic flop (or bytes) per launch / average launch duration.  Returns (dominant kernel's
+        roofline object, its HBM view, the per-kernel table)."""
+        table = self.kernel_table()
+        total_ms = sum(ms for ms, _ in prof.values()) or 1e-9
+        kernels = {}
+        for name, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            entry = {"ms_per_step": ms / steps, "launches_per_step": n / steps, "share": ms / total_ms}
+            if name in table:
+                pipe, flop, byts, _ = table[name]
+                sec = ms * 1e-3 / steps
+                entry.update({"bound": pipe, "tflops": flop * self.F / sec / 1e12, "frac": flop * self.F / sec / 1e12 / peaks[pipe + "_tflops"],
+                              "gbs": byts * self.F / sec / 1e9, "frac_hbm": byts * self.F / sec / 1e9 / hbm_peak})
+            kernels[name] = entry
+        dom = next((k for k in kernels if k in table), None)
+        if dom is None:
+            return None, None, kernels
+        pipe, flop, byts, profile = table[dom]
+        k = kernels[dom]
+        launches = max(1.0, k["launches_per_step"])
+        roof = {"bound": pipe, "achieved": k["tflops"], "peak": peaks[pipe + "_tflops"], "unit": "TFLOP/s", "frac": k["frac"],
+                "traffic": _ncu_traffic(profile) if profile else None, "kernel": dom, "flop_per_frame": flop,
+                "flop_per_launch": flop * self.F / launches, "avg_launch_ms": k["ms_per_step"] / launches, "share_of_step": k["share"],
+                "peak_source": "vbx_measure_peaks: dependent-free FMA loop on this device, this run",
+                "timing": "CUDA events on the library's stream around every launch of the timed region (vbx_profile_begin/end)"}
+        roof_hbm = {"bound": "hbm", "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["frac_hbm"],
+                    "bytes_per_frame": byts, "kernel": dom, "peak_source": hbm_src}
+        return roof, roof_hbm, kernels
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -426,10 +448,12 @@ def run_ours(args, cfg, rank, world, local_rank):
         ctx.sync()
         barrier()
         l0 = ctx.kernel_launches
+        ctx.profile_begin()  # an event after every launch: per-kernel device times for the roofline
         ctx.timer_start()
         for _ in range(args.steps):
             wl.step()
         ms = ctx.timer_stop_ms()
+        prof = ctx.profile_end()
         launches = ctx.kernel_launches - l0
         barrier()
         ms = max_over_ranks(ms)
@@ -452,7 +476,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         mp = _peaks()
         hbm_peak = mp["hbm_gbs"] if mp else 6650.0
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if mp else "fallback 6650 GB/s (of fallback)"
-        roof, roof_hbm = wl.roofline(F * args.steps / (ms * 1e-3), peaks, hbm_peak, hbm_src)
+        roof, roof_hbm, kernels = wl.roofline(prof, args.steps, peaks, hbm_peak, hbm_src)
         in_mb = audio.nbytes / 1e6
         line = {
             "metric": cfg["metric"], "value": value, "unit": "frames/s",
@@ -466,7 +490,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "e2e": {"value": total_frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d,
                     "d2h_bytes_per_step": int(wl.d2h), "steps": e2e_steps, "api": wl.api},
             "gpu_launches": int(launches),
-            "roofline": roof, "roofline_hbm": roof_hbm, "pipe_peaks": peaks,
+            "roofline": roof, "roofline_hbm": roof_hbm, "kernels": kernels, "pipe_peaks": peaks,
             "clocks": clocks.summary(),
             "checksum": checksum,
         }

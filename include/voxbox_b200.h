@@ -128,6 +128,14 @@ VBX_API int vbx_memset(vbx_ctx* ctx, void* dev, int value, size_t bytes);
 VBX_API int vbx_timer_start(vbx_ctx* ctx);
 VBX_API int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms_out); /* synchronises */
 
+/* Per-kernel device timing for roofline reports: between begin and end an event is recorded after every kernel the
+ * context launches; a kernel's time is the gap to the previous event on the stream (launches are back to back, so the
+ * few memsets / small copies in between are attributed to the kernel that follows them).  end synchronises. */
+VBX_API int vbx_profile_begin(vbx_ctx* ctx);
+VBX_API int vbx_profile_end(vbx_ctx* ctx);
+VBX_API int vbx_profile_count(vbx_ctx* ctx);
+VBX_API int vbx_profile_entry(vbx_ctx* ctx, int index, char* name_out, int name_len, double* ms_total, int64_t* launches);
+
 /* Measured pipe peaks of this device (dependent-free FMA loops on every SM), used as roofline
  * denominators for the FP32/FP64-bound kernels.  Values in TFLOP/s (2 flop per FMA). */
 VBX_API int vbx_measure_peaks(vbx_ctx* ctx, double* fp32_tflops, double* fp64_tflops);

@@ -19,6 +19,18 @@ int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...) {
     return status;
 }
 
+void vbx_prof_mark(vbx_ctx* ctx, const char* name) {
+    if (ctx->prof_used >= ctx->prof_events.size()) {
+        if (ctx->prof_events.size() >= 65536) return;  // pool exhausted: stop recording, totals stay a lower bound
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+        ctx->prof_events.push_back(e);
+    }
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream);
+    if (ctx->prof_used > 0) ctx->prof_names.push_back(name);
+    ctx->prof_used++;
+}
+
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->arena_bytes) return VBX_OK;
     // grow-only; the stream is drained first so no in-flight kernel still uses the old block
@@ -236,6 +248,7 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& kv : ctx->windows) cudaFree(kv.second);
     vbx_mfcc_cache_free(ctx);
+    for (auto e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pipe) cudaFree(ctx->pipe);
@@ -324,6 +337,42 @@ int vbx_timer_stop_ms(vbx_ctx* ctx, float* ms_out) {
     VBX_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     VBX_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
     VBX_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev_start, ctx->ev_stop));
+    return VBX_OK;
+}
+
+int vbx_profile_begin(vbx_ctx* ctx) {
+    if (!ctx) return VBX_ERR_BADARG;
+    ctx->prof_used = 0;
+    ctx->prof_names.clear();
+    ctx->prof_totals.clear();
+    ctx->prof_on = true;
+    vbx_prof_mark(ctx, "begin");
+    return VBX_OK;
+}
+
+int vbx_profile_end(vbx_ctx* ctx) {
+    if (!ctx) return VBX_ERR_BADARG;
+    ctx->prof_on = false;
+    VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 1; i < ctx->prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_events[i - 1], ctx->prof_events[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto& t = ctx->prof_totals[ctx->prof_names[i - 1]];
+        t.first += ms;
+        t.second += 1;
+    }
+    return VBX_OK;
+}
+
+int vbx_profile_count(vbx_ctx* ctx) { return ctx ? (int)ctx->prof_totals.size() : 0; }
+
+int vbx_profile_entry(vbx_ctx* ctx, int index, char* name_out, int name_len, double* ms_total, int64_t* launches) {
+    if (!ctx || index < 0 || index >= (int)ctx->prof_totals.size()) return VBX_ERR_BADARG;
+    auto it = ctx->prof_totals.begin();
+    std::advance(it, index);
+    if (name_out && name_len > 0) snprintf(name_out, name_len, "%s", it->first.c_str());
+    if (ms_total) *ms_total = it->second.first;
+    if (launches) *launches = it->second.second;
     return VBX_OK;
 }
 

@@ -38,11 +38,18 @@ struct vbx_ctx {
     size_t pipe_bytes = 0;
     // window tables (device, f64), keyed by (kind << 32 | n)
     std::map<uint64_t, double*> windows;
+    // per-kernel timing (vbx_profile_*): an event after every launch; a kernel's time = the gap to the previous event
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;   // pool, created lazily
+    std::vector<const char*> prof_names;    // name of the launch that precedes event i+1 (event 0 = begin marker)
+    size_t prof_used = 0;
+    std::map<std::string, std::pair<double, int64_t>> prof_totals;  // name -> (ms, launches)
     vbx_mfcc_cache* mfcc_cache = nullptr;
     bool mfcc_fft_f32 = false;  // MFCC transform precision (default fp64)
 };
 
 int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);
+void vbx_prof_mark(vbx_ctx* ctx, const char* name);        // records "launch `name` was just enqueued" (profiling on)
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
 int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes);          // ensures ctx->pipe has >= bytes
@@ -63,6 +70,7 @@ void vbx_window_fill_host(int kind, int n, double* out);
         if (e__ != cudaSuccess)                                                                      \
             return vbx_fail((ctx), VBX_ERR_CUDA, "launch of %s failed: %s", (name), cudaGetErrorString(e__)); \
         (ctx)->launches++;                                                                           \
+        if ((ctx)->prof_on) vbx_prof_mark((ctx), (name));                                            \
     } while (0)
 
 #define VBX_REQUIRE(ctx, cond, ...)                                                                  \

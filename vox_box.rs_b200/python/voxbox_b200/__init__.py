@@ -84,6 +84,10 @@ def _declare(L):
     sig("vbx_timer_start", C.c_int, _vp)
     sig("vbx_timer_stop_ms", C.c_int, _vp, C.POINTER(C.c_float))
     sig("vbx_measure_peaks", C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double))
+    sig("vbx_profile_begin", C.c_int, _vp)
+    sig("vbx_profile_end", C.c_int, _vp)
+    sig("vbx_profile_count", C.c_int, _vp)
+    sig("vbx_profile_entry", C.c_int, _vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64))
     sig("vbx_window_table_host", C.c_int, C.c_int, _i32, C.POINTER(C.c_double))
     sig("vbx_autocorrelate", C.c_int, _vp, _frp, _i32, _vp, _i32)
     sig("vbx_autocorrelate_host", C.c_int, _vp, _frp, _i32, _vp, _i32)
@@ -217,6 +221,20 @@ class Context:
     @property
     def sm_count(self):
         return self.lib.vbx_device_sm_count(self.h)
+
+    def profile_begin(self):
+        self._check(self.lib.vbx_profile_begin(self.h), "vbx_profile_begin")
+
+    def profile_end(self):
+        """Returns {kernel name: (total ms, launches)} for the launches since profile_begin."""
+        self._check(self.lib.vbx_profile_end(self.h), "vbx_profile_end")
+        out = {}
+        for i in range(self.lib.vbx_profile_count(self.h)):
+            name = C.create_string_buffer(128)
+            ms, n = C.c_double(0), _i64(0)
+            self._check(self.lib.vbx_profile_entry(self.h, i, name, 128, C.byref(ms), C.byref(n)), "vbx_profile_entry")
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
 
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)
