@@ -291,6 +291,13 @@ class Workload:
         np.ctypeslib.as_array(C.cast(self.h_in, C.POINTER(C.c_float)), shape=audio.shape)[...] = audio
         hfr = ctx.frames(self.h_in.value, F, N, hop, win, frames_per_segment=J, segment_stride=ns)
         self.h2d = int(audio.nbytes)
+        # the same audio as 16-bit PCM (the format the reference's WAV drivers read, tests/lib.rs:15-19): half the H2D bytes
+        pcm = np.clip(np.round(audio.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+        self.h_in16 = C.c_void_p()
+        ctx._check(L.vbx_malloc_host(h, pcm.nbytes, C.byref(self.h_in16)), "vbx_malloc_host")
+        np.ctypeslib.as_array(C.cast(self.h_in16, C.POINTER(C.c_int16)), shape=pcm.shape)[...] = pcm
+        hfr16 = ctx.frames(self.h_in16.value, F, N, hop, win, dtype=vb.I16, frames_per_segment=J, segment_stride=ns)
+        self.h2d16 = int(pcm.nbytes)
         kind = cfg["kind"]
 
         def pinned(nbytes):
@@ -304,7 +311,7 @@ class Workload:
             out_bytes = F * (p + 1) * 4
             h_r, h_ac = pinned(out_bytes), pinned(out_bytes)
             self.step = lambda: ctx._check(L.vbx_lpc(h, C.byref(fr), p, d_r.ptr, d_ac.ptr, None, vb.F32), "vbx_lpc")
-            self.e2e_step = lambda: ctx._check(L.vbx_lpc_host(h, C.byref(hfr), p, h_r, h_ac, None, vb.F32), "vbx_lpc_host")
+            self.e2e_step = lambda fr_=hfr: ctx._check(L.vbx_lpc_host(h, C.byref(fr_), p, h_r, h_ac, None, vb.F32), "vbx_lpc_host")
             self.d2h = 2 * out_bytes
             self.api = "vbx_lpc_host (pinned host buffers)"
             self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_r, C.POINTER(C.c_float)), shape=(F, p + 1))[::max(1, F // 1000), 0], dtype=np.float64))
@@ -325,9 +332,9 @@ class Workload:
                 ctx._check(L.vbx_find_formants(h, C.byref(fr), fs, p, vb.LPC_AUTOCORR, d_est.ptr, 4, d_trk.ptr, None, None, None,
                                                vb.F32), "vbx_find_formants")
 
-            def e2e_step():
+            def e2e_step(fr_=hfr):
                 C.memmove(h_est, est0.ctypes.data, est0.nbytes)
-                ctx._check(L.vbx_find_formants_host(h, C.byref(hfr), fs, p, vb.LPC_AUTOCORR, h_est, 4, h_trk, None, None, None,
+                ctx._check(L.vbx_find_formants_host(h, C.byref(fr_), fs, p, vb.LPC_AUTOCORR, h_est, 4, h_trk, None, None, None,
                                                     vb.F32), "vbx_find_formants_host")
 
             self.step, self.e2e_step = step, e2e_step
@@ -342,7 +349,7 @@ class Workload:
             d_c, d_n, d_s = ctx.empty((F, K, 2), np.float32), ctx.empty((F,), np.int32), ctx.empty((F,), np.uint8)
             h_c, h_n, h_s = pinned(F * K * 8), pinned(F * 4), pinned(F)
             self.step = lambda: ctx._check(L.vbx_pitch(h, C.byref(fr), fs, 0.45, 75.0, 600.0, K, d_c.ptr, d_n.ptr, d_s.ptr, vb.F32), "vbx_pitch")
-            self.e2e_step = lambda: ctx._check(L.vbx_pitch_host(h, C.byref(hfr), fs, 0.45, 75.0, 600.0, K, h_c, h_n, h_s, vb.F32), "vbx_pitch_host")
+            self.e2e_step = lambda fr_=hfr: ctx._check(L.vbx_pitch_host(h, C.byref(fr_), fs, 0.45, 75.0, 600.0, K, h_c, h_n, h_s, vb.F32), "vbx_pitch_host")
             self.d2h = F * (K * 8 + 5)
             self.api = "vbx_pitch_host (pinned host buffers)"
             self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_c, C.POINTER(C.c_float)), shape=(F, K * 2))[::max(1, F // 1000), 0], dtype=np.float64))
@@ -352,12 +359,14 @@ class Workload:
             d_o = ctx.empty((F, 13), np.float32)
             h_o = pinned(F * 13 * 4)
             self.step = lambda: ctx._check(L.vbx_mfcc(h, C.byref(fr), 40, 13, 133.0, 6855.0, fs, d_o.ptr, None, vb.F32), "vbx_mfcc")
-            self.e2e_step = lambda: ctx._check(L.vbx_mfcc_host(h, C.byref(hfr), 40, 13, 133.0, 6855.0, fs, h_o, vb.F32), "vbx_mfcc_host")
+            self.e2e_step = lambda fr_=hfr: ctx._check(L.vbx_mfcc_host(h, C.byref(fr_), 40, 13, 133.0, 6855.0, fs, h_o, vb.F32), "vbx_mfcc_host")
             self.d2h = F * 13 * 4
             self.api = "vbx_mfcc_host (pinned host buffers)"
             self.check = lambda: float(np.sum(np.ctypeslib.as_array(C.cast(h_o, C.POINTER(C.c_float)), shape=(F, 13))[::max(1, F // 1000), 0], dtype=np.float64))
             self.outputs = "13 MFCC per frame fp32"
             self._keep = (d_o,)
+
+        self.hfr16 = hfr16
 
     def kernel_table(self):
         """Algorithmic work per frame of every kernel of the step (SURVEY §8d figures, split per kernel):
@@ -468,7 +477,16 @@ def run_ours(args, cfg, rank, world, local_rank):
             wl.e2e_step()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
-    checksum = wl.check()
+        checksum = wl.check()
+        # the same call fed with 16-bit PCM host samples (scaled by 1/32767 on load)
+        for _ in range(2):
+            wl.e2e_step(wl.hfr16)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            wl.e2e_step(wl.hfr16)
+        e2e16_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
 
     if rank == 0:
         total_frames = F * world
@@ -489,6 +507,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                        "parallelism": f"utterance-sharded x{world}, no collective"},
             "e2e": {"value": total_frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d,
                     "d2h_bytes_per_step": int(wl.d2h), "steps": e2e_steps, "api": wl.api},
+            "e2e_pcm16": {"value": total_frames * e2e_steps / e2e16_s, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d16,
+                          "d2h_bytes_per_step": int(wl.d2h), "steps": e2e_steps,
+                          "note": "same call, host samples as int16 PCM (vbx_frames.dtype = VBX_I16)"},
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_hbm": roof_hbm, "kernels": kernels, "pipe_peaks": peaks,
             "clocks": clocks.summary(),

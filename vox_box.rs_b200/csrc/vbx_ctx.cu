@@ -116,8 +116,9 @@ void vbx_window_fill_host(int kind, int n, double* out) {
     }
 }
 
-int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out) {
-    uint64_t key = ((uint64_t)(uint32_t)kind << 32) | (uint32_t)n;
+int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out, int sample_dtype) {
+    const bool pcm = (sample_dtype == VBX_I16);
+    uint64_t key = ((uint64_t)(uint32_t)(kind | (pcm ? 0x100 : 0)) << 32) | (uint32_t)n;
     auto it = ctx->windows.find(key);
     if (it != ctx->windows.end()) {
         *dev_out = it->second;
@@ -125,6 +126,8 @@ int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out) {
     }
     std::vector<double> host(n);
     vbx_window_fill_host(kind, n, host.data());
+    if (pcm)
+        for (auto& v : host) v = v / 32767.0;  // sample / 32767 · w  ==  sample · (w / 32767) to an ulp of f64
     double* dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, (size_t)n * sizeof(double));
     if (e != cudaSuccess) {

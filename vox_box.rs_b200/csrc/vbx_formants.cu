@@ -200,7 +200,7 @@ template <typename TIn> burg_kernel_t pick_burg(int c_needed, int* c_out) {
 template <typename TIn>
 int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uint8_t* status_out, int out_dtype) {
     const double* win = nullptr;
-    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win);
+    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win, fr->dtype);
     if (st != VBX_OK) return st;
     BurgParams P;
     P.base = fr->base; P.win = win; P.coeffs_out = coeffs_out; P.status_out = status_out;

@@ -53,7 +53,9 @@ void vbx_prof_mark(vbx_ctx* ctx, const char* name);        // records "launch `n
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
 int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes);          // ensures ctx->pipe has >= bytes
-int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out);  // cached device table (ones for NONE)
+// cached device table (ones for NONE).  sample_dtype == VBX_I16 folds the PCM scale into the table: w[i] / 32767
+// (tests/lib.rs:17-19 scale every sample by 1/(i32::MAX >> 16) before any arithmetic).
+int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out, int sample_dtype = VBX_F32);
 void vbx_window_fill_host(int kind, int n, double* out);
 
 #define VBX_CUDA(ctx, call)                                                                          \
@@ -98,7 +100,7 @@ static inline int64_t vbx_frames_extent(const vbx_frames* fr) {
 #ifdef __CUDACC__
 template <typename T> __device__ __forceinline__ T vbx_ldg(const T* p) { return __ldg(p); }
 
-// sample load with dtype dispatch (F32, or I16 PCM scaled by 1/32767 — tests/lib.rs:17-19)
+// sample load with dtype dispatch (F32, or raw I16 PCM: the 1/32767 scale lives in the window table, vbx_get_window)
 template <typename TIn> __device__ __forceinline__ float vbx_load_sample(const TIn* p);
 template <> __device__ __forceinline__ float vbx_load_sample<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float vbx_load_sample<int16_t>(const int16_t* p) { return (float)__ldg(p); }

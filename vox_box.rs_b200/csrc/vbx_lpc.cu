@@ -137,6 +137,32 @@ __global__ void __launch_bounds__(kMaxThreads, (L <= 13 ? 5 : 1)) lpc_fused_kern
             }
             done = n4 << 2;
         }
+        if (sizeof(TIn) == 2 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            // int16 PCM: 16-byte loads of 8 samples, 4 in flight per thread
+            const uint4* src8 = reinterpret_cast<const uint4*>(src);
+            const int n8 = total >> 3;
+            for (int v0 = tid; v0 < n8; v0 += 4 * nthreads) {
+                uint4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * nthreads;
+                    if (v < n8) a[u] = __ldg(src8 + v);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * nthreads;
+                    if (v < n8) {
+                        const unsigned w[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            s_span[phys(8 * v + 2 * h)] = (float)(short)(w[h] & 0xffffu);
+                            s_span[phys(8 * v + 2 * h + 1)] = (float)(short)(w[h] >> 16);
+                        }
+                    }
+                }
+            }
+            done = n8 << 3;
+        }
         for (int s0 = done + tid; s0 < total; s0 += 8 * nthreads) {
             float a[8];
 #pragma unroll
@@ -427,7 +453,7 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
         filled = true;
     }
     const double* win = nullptr;
-    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win);
+    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win, fr->dtype);
     if (st != VBX_OK) return st;
 
     LpcParams P;

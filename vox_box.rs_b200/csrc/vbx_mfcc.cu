@@ -354,7 +354,7 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
                 void* energies_out, int out_dtype) {
     const int n = fr->frame_len;
     const double* win = nullptr;
-    int st = vbx_get_window(ctx, fr->window, n, &win);
+    int st = vbx_get_window(ctx, fr->window, n, &win, fr->dtype);
     if (st != VBX_OK) return st;
     const MfccTables* t = nullptr;
     st = get_tables(ctx, n, num_coeffs, n_keep, f_lo, f_hi, fs, &t);

@@ -644,7 +644,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     const int n = fr->frame_len;
     const double* win = nullptr;
     const double* lagwin = nullptr;
-    int st = vbx_get_window(ctx, fr->window, n, &win);
+    int st = vbx_get_window(ctx, fr->window, n, &win, fr->dtype);
     if (st != VBX_OK) return st;
     st = vbx_get_window(ctx, VBX_WINDOW_HANN_LAG, n, &lagwin);
     if (st != VBX_OK) return st;
