@@ -154,3 +154,30 @@ def test_waves_nan_semantics(oracle):
     got = c.max_amplitude(x)
     assert got[0] == 3.0 and np.isnan(got[1])
     assert got[0] == oracle.max_amplitude(x[0]) and np.isnan(oracle.max_amplitude(x[1]))
+
+
+@pytest.mark.parametrize("N", [160, 200, 256, 320, 400, 480, 512, 640, 800, 1024])
+def test_mfcc_fast_kernels_every_specialised_length(oracle, N, monkeypatch):
+    """Every frame length with a specialised warp-per-frame kernel (vbx_mfcc_fast.cuh), fp64 and fp32 transforms, a frame
+    count that leaves a ragged last group, against the oracle and against the any-length CTA kernel."""
+    fs = 16000
+    audio = synth.utterance(60 + N % 7, fs, seconds=1.2)
+    c = ctx()
+    hop = N // 2
+    F = min(c.n_frames_of(audio.size, N, hop), 37)
+    d = c.to_device(audio)
+    fr = c.frames(d.ptr, F, N, hop, vb.WINDOW_HANN_SYMMETRIC)
+    hi = 7000.0 if N >= 256 else 6000.0
+    out = c.mfcc(fr, 26, 100.0, hi, float(fs), n_keep=13).to_host()
+    ref = oracle.batch_mfcc(audio, F, N, hop, oracle.WIN_HANN_SYMMETRIC, 26, 100.0, hi, float(fs), n_keep=13, n_threads=0)
+    assert normwise(out, ref).max() < 1e-9
+    monkeypatch.setenv("VBX_MFCC_GENERIC", "1")
+    gen = c.mfcc(fr, 26, 100.0, hi, float(fs), n_keep=13).to_host()
+    monkeypatch.delenv("VBX_MFCC_GENERIC")
+    assert normwise(out, gen).max() < 1e-12
+    c.mfcc_set_fft_precision(vb.F32)
+    try:
+        out32 = c.mfcc(fr, 26, 100.0, hi, float(fs), n_keep=13).to_host()
+    finally:
+        c.mfcc_set_fft_precision(vb.F64)
+    assert np.median(normwise(out32, ref)) < 1e-6

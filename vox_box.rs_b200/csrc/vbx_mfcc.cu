@@ -55,6 +55,8 @@ template <typename R> __device__ __forceinline__ cxt<R> csubf(cxt<R> a, cxt<R> b
 template <typename R> __device__ __forceinline__ cxt<R> mulnegi(cxt<R> a) { return mk<R>(a.y, -a.x); }  // (−i)·a
 
 // one radix-R Stockham butterfly: inputs src[j + t·T], twiddled by W_{Ls·R}^{k·t}, outputs dst[(j−k)·R + k + u·Ls]
+#include "vbx_mfcc_fast.cuh"  // inside the anonymous namespace: uses cxt<> and the complex helpers above
+
 template <int R, typename TR>
 __device__ __forceinline__ void butterfly(const cxt<TR>* __restrict__ src, cxt<TR>* __restrict__ dst, const cxt<TR>* __restrict__ tw,
                                           int j, int T, int Ls, int tw_stride /* N / (Ls·R) */) {
@@ -349,6 +351,53 @@ bool plan_radices(int mc, int* radix, int* n_pass) {
     return m == 1;
 }
 
+// ---- specialised warp-per-frame kernels for the common even frame lengths (vbx_mfcc_fast.cuh) ------------------------
+template <typename TIn, typename TR, int MC, int R0, int R1, int R2, int R3, int FW>
+int launch_fast_one(vbx_ctx* ctx, const mfcc_fast::FastParams& Q) {
+    constexpr int N = 2 * MC, MS = MC + 1;
+    const size_t cs = sizeof(TR) * 2;
+    int warps = 4;
+    constexpr int WB = FW * MS + ((FW * MS) >> 3) + 1;
+    auto bytes = [&](int w) {
+        return (size_t)N * cs + (size_t)w * WB * cs + ((size_t)Q.n_keep * Q.num_coeffs + (size_t)w * FW * Q.num_coeffs) * sizeof(double);
+    };
+    while (warps > 1 && bytes(warps) > 56 * 1024) --warps;  // 4 CTAs / SM
+    const size_t smem = bytes(warps);
+    VBX_REQUIRE(ctx, smem <= ctx->smem_optin, "MFCC: shared memory");
+    auto kern = mfcc_fast::mfcc_warp_kernel<TIn, TR, MC, R0, R1, R2, R3, FW>;
+    VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const int64_t n_groups = (Q.n_frames + FW - 1) / FW;
+    int64_t grid = (n_groups + warps - 1) / warps;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;  // persistent: warps loop over frame groups
+    if (grid > cap) grid = cap;
+    kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(Q);
+    VBX_CHECK_LAUNCH(ctx, "mfcc_kernel");
+    return VBX_OK;
+}
+
+// returns 1 if a specialisation handled the call, 0 if none exists for this frame length, < 0 on error (−status)
+template <typename TIn, typename TR>
+int launch_fast(vbx_ctx* ctx, int n, const mfcc_fast::FastParams& Q) {
+    int st;
+    switch (n) {
+#define VBX_MFCC_CASE(NN, R0, R1, R2, R3, FW) \
+    case NN: st = launch_fast_one<TIn, TR, NN / 2, R0, R1, R2, R3, FW>(ctx, Q); return st == VBX_OK ? 1 : -st;
+        VBX_MFCC_CASE(160, 8, 5, 2, 1, 4)
+        VBX_MFCC_CASE(200, 5, 5, 4, 1, 4)
+        VBX_MFCC_CASE(256, 8, 4, 4, 1, 4)
+        VBX_MFCC_CASE(320, 8, 5, 4, 1, 2)
+        VBX_MFCC_CASE(400, 8, 5, 5, 1, 2)
+        VBX_MFCC_CASE(480, 8, 5, 3, 2, 2)
+        VBX_MFCC_CASE(512, 8, 8, 4, 1, 2)
+        VBX_MFCC_CASE(640, 8, 8, 5, 1, 2)
+        VBX_MFCC_CASE(800, 8, 5, 5, 2, 1)
+        VBX_MFCC_CASE(1024, 8, 8, 8, 1, 1)
+#undef VBX_MFCC_CASE
+    default: return 0;
+    }
+}
+
 template <typename TIn>
 int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, double f_lo, double f_hi, double fs, void* out,
                 void* energies_out, int out_dtype) {
@@ -392,6 +441,16 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
     // fp32 FFT's ~1e-6 relative error then exceeds the 1e-5 norm-wise bound on quiet frames); fp32 is opt-in
     bool f32 = ctx->mfcc_fft_f32;
     if (const char* e = getenv("VBX_MFCC_FFT")) f32 = (e[0] == 'f' && e[1] == '3');
+    if (P.mode == 0 && !getenv("VBX_MFCC_GENERIC") && P.kmax <= n && num_coeffs <= 128 && n_keep * num_coeffs <= 2048) {
+        mfcc_fast::FastParams Q;
+        Q.base = P.base; Q.win = P.win; Q.tw = P.tw; Q.wu = P.wu; Q.wd = P.wd; Q.bins = P.bins; Q.dct = P.dct;
+        Q.out = P.out; Q.energies_out = P.energies_out;
+        Q.n_frames = P.n_frames; Q.stride = P.stride; Q.seg_frames = P.seg_frames; Q.seg_stride = P.seg_stride;
+        Q.num_coeffs = num_coeffs; Q.n_keep = n_keep; Q.klo = P.klo; Q.khi = P.khi; Q.out_f64 = P.out_f64; Q.warps_per_cta = 0;
+        const int r = f32 ? launch_fast<TIn, float>(ctx, n, Q) : launch_fast<TIn, double>(ctx, n, Q);
+        if (r < 0) return -r;
+        if (r == 1) return VBX_OK;
+    }
     const size_t cs = f32 ? sizeof(float) * 2 : sizeof(double) * 2;
     // frames per CTA: as many as fit ~56 KB of shared memory (4 CTAs / SM), at most 16
     const size_t fixed = (size_t)n * cs;
