@@ -359,7 +359,7 @@ int launch_fast_one(vbx_ctx* ctx, const mfcc_fast::FastParams& Q) {
     int warps = 4;
     constexpr int WB = FW * MS + ((FW * MS) >> 3) + 1;
     auto bytes = [&](int w) {
-        return (size_t)N * cs + (size_t)w * WB * cs + ((size_t)Q.n_keep * Q.num_coeffs + (size_t)w * FW * Q.num_coeffs) * sizeof(double);
+        return (size_t)N * cs + (size_t)w * WB * cs + ((size_t)Q.n_keep * Q.num_coeffs + 2 * (size_t)N + (size_t)w * FW * Q.num_coeffs) * sizeof(double);
     };
     while (warps > 1 && bytes(warps) > 56 * 1024) --warps;  // 4 CTAs / SM
     const size_t smem = bytes(warps);

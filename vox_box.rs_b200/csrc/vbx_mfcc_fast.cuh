@@ -155,12 +155,15 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
     constexpr int WB = FW * MS + ((FW * MS) >> 3) + 1;                            // padded elements per warp
     C* buf = s_tw + N + (size_t)warp * WB;                                       // per warp: FW rows of MS (+ padding)
     double* s_dct = reinterpret_cast<double*>(s_tw + N + (size_t)nwarps * WB);   // [n_keep][M] cosine table (CTA wide)
-    double* s_e = s_dct + (size_t)P.n_keep * M + (size_t)warp * FW * M;            // [FW][M]
+    double* s_wu = s_dct + (size_t)P.n_keep * M;                                   // [N] up-slope weights
+    double* s_wd = s_wu + N;                                                       // [N] down-slope weights
+    double* s_e = s_wd + N + (size_t)warp * FW * M;                                // [FW][M]
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const double2 w = __ldg(P.tw + i);
         s_tw[i] = mk<TR>((TR)w.x, (TR)w.y);
     }
     for (int i = threadIdx.x; i < P.n_keep * M; i += blockDim.x) s_dct[i] = __ldg(P.dct + i);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { s_wu[i] = __ldg(P.wu + i); s_wd[i] = __ldg(P.wd + i); }
     __syncthreads();
 
     const int64_t n_groups = (P.n_frames + FW - 1) / FW;
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
             const int pk0 = q * MS;
             const int b0 = __ldg(P.bins + w), b1 = __ldg(P.bins + w + 1), b2 = __ldg(P.bins + w + 2);
             double up = 0., down = 0.;
-            for (int k = b0; k < b1; ++k) up = up + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].x * __ldg(P.wu + k);
-            for (int k = b1; k < b2; ++k) down = down + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].y * __ldg(P.wd + k);
+            for (int k = b0; k < b1; ++k) up = up + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].x * s_wu[k];
+            for (int k = b1; k < b2; ++k) down = down + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].y * s_wd[k];
             double e = log10(up + down);
             e = (e > 1.0e-10) ? e : 1.0e-10;  // f64::max(1e-10): NaN → 1e-10
             s_e[q * M + w] = e;
