@@ -166,8 +166,18 @@ def make_corpus(cfg, rank):
 # ------------------------------------------------------------------------------------------------
 # CPU port (oracle) of each config: used by --impl reference and by the cpu_baseline leg
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Host threads for the CPU arm: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
+    would silently make the "all host threads" baseline single-threaded, so the count is passed explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_pass(cfg, audio_rows, J, n_threads):
-    """One pass of the reference's per-frame loop over the given utterances on the CPU oracle."""
+    """One pass of the reference's per-frame loop over the given utterances on the CPU oracle (n_threads: 1 = as
+    shipped, >1 = OpenMP over frames / utterances)."""
     import oracle
     N, hop, fs = cfg["n"], cfg["hop"], float(cfg["fs"])
     kind = cfg["kind"]
@@ -210,7 +220,7 @@ def run_reference(args, cfg, rank, world):
         return
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     sub = dict(cfg)
     sub["utts"] = sub["distinct"] = cpu_sample_utts(cfg, threads)
     audio = make_corpus(sub, 0)
@@ -218,10 +228,10 @@ def run_reference(args, cfg, rank, world):
     rows = list(audio)
 
     for _ in range(args.warmup):
-        cpu_pass(cfg, rows, J, 0)
+        cpu_pass(cfg, rows, J, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_pass(cfg, rows, J, 0)
+        cpu_pass(cfg, rows, J, threads)
     dt = time.perf_counter() - t0
     frames = len(rows) * J * args.steps
     value = frames / dt
@@ -248,7 +258,7 @@ def cpu_baseline(cfg, rank_audio):
     import oracle
     oracle.build()
     J = oracle.n_frames_of(rank_audio.shape[1], cfg["n"], cfg["hop"])
-    threads = oracle.max_threads()
+    threads = host_threads()
     n_all = min(cpu_sample_utts(cfg, threads), rank_audio.shape[0])
     n_one = max(1, min(n_all, {"lpc": 20, "formants": 3, "pitch": 1, "mfcc": 6}[cfg["kind"]]))
     rows = list(rank_audio[:n_all])
@@ -258,7 +268,7 @@ def cpu_baseline(cfg, rank_audio):
     reps = 0
     t0 = time.perf_counter()
     while True:
-        cpu_pass(cfg, rows, J, 0)
+        cpu_pass(cfg, rows, J, threads)
         reps += 1
         if time.perf_counter() - t0 > 3.0 or reps >= 50:
             break
@@ -429,7 +439,20 @@ def run_ours(args, cfg, rank, world, local_rank):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout while the communicator is created: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if dist is not None:
