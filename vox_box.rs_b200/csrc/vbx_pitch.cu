@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) pitch_refine_kernel(const PitchParams P) 
 //
 // Lane ℓ8 of a slot owns the terms n ≡ ℓ8 (mod 8) of both sides of interpolate_sinc's sum, so that per term
 //   * (−1)ⁿ is a per-lane constant (stride 8 is even),
-//   * the Hann factor ½ + ½cos(π(φ+n)/(φ+D)) advances by a fixed rotation (cos 8δ, sin 8δ), δ = π/(φ+D),
+//   * the Hann factor ½ + ½cos(π(φ+n)/(φ+D)) advances by a three-term recurrence in cos 8δ, δ = π/(φ+D),
 //   * the two sides share one reciprocal: y_l·h_l/t_l + y_r·h_r/t_r = (y_l·h_l·t_r + y_r·h_r·t_l)/(t_l·t_r).
 // The four slots of a warp hold consecutive work-list entries (same frame, ascending lag, hence similar depth D)
 // and run Brent in lockstep; the term loop runs to the largest D of the four, shorter slots are masked.
@@ -408,6 +408,15 @@ __device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positiv
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// one Newton step on the 20-bit MUFU seed: relative error <= 1e-12 (tools/cuda/rcp_test.cu, measured on B200) — far below
+// the ~3e-8 the fp32 lag sweep leaves in the lag function this weight multiplies
+__device__ __forceinline__ double rcp_pos1(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
 
@@ -472,15 +481,19 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
             const bool act = !special;
             const double pl = act ? phil : 0.5, pr = act ? phir : 0.5;
             const double Dd = (double)(D < 0 ? 0 : D);
-            const double inv_l = 1.0 / (pl + Dd), inv_r = 1.0 / (pr + Dd);
-            double s0, c_unused;
-            sincospi(pl, &s0, &c_unused);
+            const double inv_l = rcp_pos(pl + Dd), inv_r = rcp_pos(pr + Dd);
+            const double s0 = sinpi(pl);
             double S8l, C8l, S8r, C8r, sl, cl, sr, cr;
             sincospi(8.0 * inv_l, &S8l, &C8l);
             sincospi(8.0 * inv_r, &S8r, &C8r);
             double tl = pl + (double)l8, tr = pr + (double)l8;
             sincospi(tl * inv_l, &sl, &cl);
             sincospi(tr * inv_r, &sr, &cr);
+            // Hann factor h_j = ½ + ½cos(θ0 + 8δ·j) by the three-term recurrence h_{j+1} = K·h_j − h_{j−1} + (1 − K/2),
+            // K = 2cos 8δ (error growth ~j²·ε, j <= 150), started from h_0 and h_{−1} = ½ + ½cos(θ0 − 8δ)
+            double hl = fma(0.5, cl, 0.5), hlp = fma(0.5, fma(cl, C8l, sl * S8l), 0.5);
+            double hr = fma(0.5, cr, 0.5), hrp = fma(0.5, fma(cr, C8r, sr * S8r), 0.5);
+            const double Kl = 2.0 * C8l, Kr = 2.0 * C8r, Cl = 1.0 - C8l, Cr = 1.0 - C8r;
             const int L = offset + nr, R = offset + nl;
             const int Dmax = __reduce_max_sync(FULL, D);
             double acc = 0.;
@@ -492,13 +505,11 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
                 ir = ir < 0 ? 0 : ir;
                 const double yl = (on && il < N) ? __ldg(y + il) : 0.0;
                 const double yr = (on && ir < N) ? __ldg(y + ir) : 0.0;
-                const double hl = fma(0.5, cl, 0.5), hr = fma(0.5, cr, 0.5);
                 const double num = fma(yl * hl, tr, (yr * hr) * tl);
                 acc = fma(num, rcp_pos(tl * tr), acc);
-                // advance: t += 8, rotate the Hann phase by 8δ
-                const double ncl = fma(cl, C8l, -(sl * S8l)), nsl = fma(sl, C8l, cl * S8l);
-                const double ncr = fma(cr, C8r, -(sr * S8r)), nsr = fma(sr, C8r, cr * S8r);
-                cl = ncl; sl = nsl; cr = ncr; sr = nsr;
+                // advance: t += 8, Hann factors one recurrence step
+                const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
+                hlp = hl; hl = nhl; hrp = hr; hr = nhr;
                 tl += 8.0; tr += 8.0;
             }
             acc *= sgn;
