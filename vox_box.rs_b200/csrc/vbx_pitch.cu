@@ -411,15 +411,8 @@ __device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positiv
     return fma(r, e, r);
 }
 
-// one Newton step on the 20-bit MUFU seed: relative error <= 1e-12 (tools/cuda/rcp_test.cu, measured on B200) — far below
-// the ~3e-8 the fp32 lag sweep leaves in the lag function this weight multiplies
-__device__ __forceinline__ double rcp_pos1(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
+// (A single Newton step would leave 1e-12 relative error — tools/cuda/rcp_test.cu — and that already moves some weak
+// candidates' Brent paths by > 0.1 Hz in tests/test_gpu_pitch.py, so the reciprocal keeps both steps.)
 __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;

@@ -181,16 +181,47 @@ __global__ void __launch_bounds__(128) lpc_roots_kernel(const RootsParams Q) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kRootsThreads = 128;
 
+// Laguerre update (polynomial.rs:48-69) from the Horner triple (a0, a1, a2) = (P, P', P''/2) at z: returns the step n/cc.
+// FAST (fp32 path, polished in fp64 afterwards): one reciprocal per complex division instead of two IEEE divisions and
+// squared magnitudes for the |cc1| > |cc2| choice; the fp64 path keeps the reference's operations one for one.
+template <typename TR, bool FAST>
+__device__ __forceinline__ vcx<TR> laguerre_step(vcx<TR> a0, vcx<TR> a1, vcx<TR> a2, TR nn, TR nref) {
+    if (FAST) {
+        const TR inv0 = (TR)1 / cnorm_sqr(a0);
+        const vcx<TR> ca = cmk<TR>(-(a1.re * a0.re + a1.im * a0.im) * inv0, -(a1.im * a0.re - a1.re * a0.im) * inv0);
+        const vcx<TR> ca2 = cmul(ca, ca);
+        const vcx<TR> t2 = cmk<TR>((TR)2 * (a2.re * a0.re + a2.im * a0.im) * inv0, (TR)2 * (a2.im * a0.re - a2.re * a0.im) * inv0);
+        const vcx<TR> cb = csub(ca2, t2);
+        const vcx<TR> c1 = csqrt_principal(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
+        const vcx<TR> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
+        const TR n1 = cnorm_sqr(cc1), n2 = cnorm_sqr(cc2);
+        const vcx<TR> den = (n1 > n2) ? cc1 : cc2;
+        const TR invd = nref / ((n1 > n2) ? n1 : n2);
+        return cmk<TR>(den.re * invd, -den.im * invd);  // n / den = n·conj(den)/|den|²
+    } else {
+        const vcx<TR> ca = cdiv(cneg(a1), a0);
+        const vcx<TR> ca2 = cmul(ca, ca);
+        const vcx<TR> t2 = cdiv(cmk<TR>((TR)2 * a2.re, (TR)2 * a2.im), a0);
+        const vcx<TR> cb = csub(ca2, t2);
+        const vcx<TR> c1 = csqrt_principal(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
+        const vcx<TR> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
+        const vcx<TR> den = (cnorm(cc1) > cnorm(cc2)) ? cc1 : cc2;
+        return cdiv(cmk<TR>(nref, (TR)0), den);
+    }
+}
+
 template <typename TR>
 __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const RootsParams Q, const int P) {
     extern __shared__ __align__(16) unsigned char roots_smem[];
     constexpr int T = kRootsThreads;
+    const unsigned FULL = 0xffffffffu;
     double* a_s = reinterpret_cast<double*>(roots_smem);                    // [P+1][T] original real coefficients
     vcx<TR>* c_s = reinterpret_cast<vcx<TR>*>(a_s + (size_t)(P + 1) * T);   // [P+1][T] working polynomial
     vcx<TR>* r_s = c_s + (size_t)(P + 1) * T;                               // [P][T]   roots in find_roots order
     const int tid = threadIdx.x;
-    const int64_t f = (int64_t)blockIdx.x * T + tid;
-    if (f >= Q.n_frames) return;
+    const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
+    const bool in_range = f_raw < Q.n_frames;
+    const int64_t f = in_range ? f_raw : Q.n_frames - 1;  // out-of-range lanes shadow the last frame (no stores): warp-wide ops stay full
     const int R = Q.R;
     auto write_res = [&](int slot, double fr_, double bw_) {
         if (Q.out_f64) {
@@ -210,12 +241,7 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
             o[0] = (float)z.re; o[1] = (float)z.im;
         }
     };
-    if (Q.status_in && Q.status_in[f] != VBX_OK) {  // the LPC stage failed: find_formants returns Err before root finding
-        if (Q.status_out) Q.status_out[f] = Q.status_in[f];
-        if (Q.nres_out) Q.nres_out[f] = 0;
-        if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
-        return;
-    }
+    const bool lpc_failed = Q.status_in && Q.status_in[f] != VBX_OK;  // find_formants returns Err before root finding
     // polynomial in ascending powers: a[k] = coefficient of z^k = lpc_{P-k}, a[P] = 1   (lib.rs:78-91)
     auto lpc_at = [&](int idx) -> double {
         return Q.lpc_f64 ? reinterpret_cast<const double*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx]
@@ -228,46 +254,66 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     }
     constexpr bool FAST = (sizeof(TR) == 4);
     const TR nn = (TR)((P - 1) * P), nref = (TR)P;
-    // polynomial.rs:116-128: for m = P down to 3: z = laguerre(coeffs, −2−2i); deflate
+    // polynomial.rs:116-128: for m = P down to 3: z = laguerre(coeffs, −2−2i); deflate.  The (degree, iteration)
+    // loops are flattened: every lane carries its own degree M and iteration count, so a lane that converges early
+    // deflates and starts its next solve at once instead of idling until the slowest lane of the warp is done.  One
+    // trip = one Laguerre iteration for every lane; Horner starts at the warp's largest M — the coefficients above a
+    // lane's own degree are exact zeros, so the extra steps change nothing (0·z + c = c).
+    int M = P, it = 0;
+    vcx<TR> z = cmk<TR>((TR)-2, (TR)-2);
+    bool active = (P >= 3) && !lpc_failed;
 #pragma unroll 1
-    for (int M = P; M >= 3; --M) {
-        vcx<TR> z = cmk<TR>((TR)-2, (TR)-2);
-#pragma unroll 1
-        for (int it = 0; it < 20; ++it) {
-            vcx<TR> a0 = c_s[M * T + tid], a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
+    while (true) {
+        const int Mmax = __reduce_max_sync(FULL, active ? M : 0);
+        if (Mmax < 3) break;
+        vcx<TR> a0 = c_s[Mmax * T + tid], a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
 #pragma unroll 4
-            for (int j = M - 1; j >= 0; --j) {
-                const vcx<TR> cj = c_s[j * T + tid];
-                a2 = cfma(a2, z, a1);
-                a1 = cfma(a1, z, a0);
-                a0 = cfma(a0, z, cj);
-            }
-            if (cnorm(a0) <= (TR)1.0e-16) break;
-            const vcx<TR> ca = cdiv(cneg(a1), a0);
-            const vcx<TR> ca2 = cmul(ca, ca);
-            const vcx<TR> t2 = cdiv(cmk<TR>((TR)2 * a2.re, (TR)2 * a2.im), a0);
-            const vcx<TR> cb = csub(ca2, t2);
-            const vcx<TR> c1 = csqrt_principal(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
-            const vcx<TR> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
-            const vcx<TR> den = (cnorm(cc1) > cnorm(cc2)) ? cc1 : cc2;
-            const vcx<TR> step = cdiv(cmk<TR>(nref, (TR)0), den);
-            z = cadd(z, step);
-            if (FAST) {  // converged for the purpose of the fp64 polish that follows
-                const TR eps = (TR)3.0e-7;
-                if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) break;
-            }
+        for (int j = Mmax - 1; j >= 0; --j) {
+            const vcx<TR> cj = c_s[j * T + tid];
+            a2 = cfma(a2, z, a1);
+            a1 = cfma(a1, z, a0);
+            a0 = cfma(a0, z, cj);
         }
-        r_s[(P - M) * T + tid] = z;
-        // deflation by the root (polynomial.rs:155-195 with other = −z)
-        vcx<TR> carry = c_s[M * T + tid];
-        c_s[M * T + tid] = cmk<TR>((TR)0, (TR)0);
+        if (active) {
+            bool done = false;
+            if (cnorm_sqr(a0) <= (TR)1.0e-32) {  // |P(z)| <= 1e-16 (polynomial.rs:47)
+                done = true;
+            } else {
+                const vcx<TR> step = laguerre_step<TR, FAST>(a0, a1, a2, nn, nref);
+                z = cadd(z, step);
+                if (FAST) {  // converged for the purpose of the fp64 polish that follows
+                    const TR eps = (TR)3.0e-7;
+                    if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) done = true;
+                }
+                if (++it == 20) done = true;
+            }
+            if (done) {
+                r_s[(P - M) * T + tid] = z;
+                // deflation by the root (polynomial.rs:155-195 with other = −z)
+                vcx<TR> carry = c_s[M * T + tid];
+                c_s[M * T + tid] = cmk<TR>((TR)0, (TR)0);
 #pragma unroll 4
-        for (int i = M - 1; i >= 0; --i) {
-            const vcx<TR> old = c_s[i * T + tid];
-            c_s[i * T + tid] = carry;
-            carry = cmk<TR>(old.re + (carry.re * z.re - carry.im * z.im), old.im + (carry.re * z.im + carry.im * z.re));
+                for (int i = M - 1; i >= 0; --i) {
+                    const vcx<TR> old = c_s[i * T + tid];
+                    c_s[i * T + tid] = carry;
+                    carry = cmk<TR>(old.re + (carry.re * z.re - carry.im * z.im), old.im + (carry.re * z.im + carry.im * z.re));
+                }
+                --M;
+                it = 0;
+                z = cmk<TR>((TR)-2, (TR)-2);
+                active = (M >= 3);
+            }
         }
     }
+    if (lpc_failed) {
+        if (in_range) {
+            if (Q.status_out) Q.status_out[f] = Q.status_in[f];
+            if (Q.nres_out) Q.nres_out[f] = 0;
+            if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
+        }
+        return;
+    }
+    if (!in_range) return;
     if (P >= 2) {
         // polynomial.rs:131-139 quadratic tail: (−c1 ± sqrt(c1² − 4 c2 c0)) / 2c2, "+" first
         const vcx<TR> q0 = c_s[tid], q1 = c_s[T + tid], q2 = c_s[2 * T + tid];
