@@ -47,44 +47,6 @@ template <typename T> __device__ __forceinline__ vcx<T> csqrt_principal(vcx<T> a
     return cmk<T>(re, im);
 }
 
-// One Laguerre solve on c[0..=M] (degree M, ascending powers) with the reference's fixed `n = NREF`
-// (the slice length − 1, polynomial.rs:35 — never the deflated degree) and
-// c1 = sqrt((n−1)·n·cb − ca2).  Coefficients above M are zero in the reference's buffer, so starting
-// Horner at M is arithmetically identical.  Up to 20 iterations, exit only if |P(z)| <= 1e-16.
-// FAST adds a convergence exit (|Δz| tiny relative to |z|) for the fp32 path, whose result is
-// polished in fp64 afterwards.
-template <typename T, int M, int NREF, bool FAST>
-__device__ __forceinline__ vcx<T> laguerre_solve(const vcx<T>* c, vcx<T> z, int* iters_out = nullptr) {
-    int it = 0;
-    for (; it < 20; ++it) {
-        vcx<T> a0 = c[M], a1 = cmk<T>((T)0, (T)0), a2 = cmk<T>((T)0, (T)0);
-#pragma unroll
-        for (int j = M - 1; j >= 0; --j) {
-            a2 = cfma(a2, z, a1);
-            a1 = cfma(a1, z, a0);
-            a0 = cfma(a0, z, c[j]);
-        }
-        if (cnorm(a0) <= (T)1.0e-16) break;
-        const vcx<T> ca = cdiv(cneg(a1), a0);
-        const vcx<T> ca2 = cmul(ca, ca);
-        const vcx<T> t2 = cdiv(cmk<T>((T)2 * a2.re, (T)2 * a2.im), a0);
-        const vcx<T> cb = csub(ca2, t2);
-        const T nn = (T)((NREF - 1) * NREF);
-        const vcx<T> c1 = csqrt_principal(cmk<T>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
-        const vcx<T> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
-        const vcx<T> den = (cnorm(cc1) > cnorm(cc2)) ? cc1 : cc2;
-        const vcx<T> step = cdiv(cmk<T>((T)NREF, (T)0), den);
-        z = cadd(z, step);
-        if (FAST) {
-            // converged for the purpose of the fp64 polish that follows
-            const T eps = (sizeof(T) == 4) ? (T)3.0e-7 : (T)1.0e-15;
-            if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) { ++it; break; }
-        }
-    }
-    if (iters_out) *iters_out = it;
-    return z;
-}
-
 // Runtime-degree variant (generic find_roots path): c has `len` entries, n = len − 1.
 template <typename T> __device__ inline vcx<T> laguerre_solve_rt(const vcx<T>* c, int len, vcx<T> z) {
     const int n = len - 1;
@@ -104,36 +66,6 @@ template <typename T> __device__ inline vcx<T> laguerre_solve_rt(const vcx<T>* c
         const vcx<T> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
         const vcx<T> den = (cnorm(cc1) > cnorm(cc2)) ? cc1 : cc2;
         z = cadd(z, cdiv(cmk<T>((T)n, (T)0), den));
-    }
-    return z;
-}
-
-// Deflation by the root z (polynomial.rs:155-195 with other = −z): q[i] = c[i+1] + z·q[i+1],
-// q[M−1] = c[M]; the quotient replaces c[0..M) and c[M] becomes 0.
-template <typename T, int M> __device__ __forceinline__ void deflate(vcx<T>* c, vcx<T> z) {
-    vcx<T> carry = c[M];
-    c[M] = cmk<T>((T)0, (T)0);
-#pragma unroll
-    for (int i = M - 1; i >= 0; --i) {
-        const vcx<T> old = c[i];
-        c[i] = carry;
-        // rem[i] = rem[i] − self[i]·other, other = −z  ⇒  rem[i] = old + carry·z
-        carry = cmk<T>(old.re + (carry.re * z.re - carry.im * z.im), old.im + (carry.re * z.im + carry.im * z.re));
-    }
-}
-
-// Two fp64 Newton steps on the ORIGINAL real-coefficient polynomial a[0..=P] (ascending powers).
-template <int P> __device__ __forceinline__ vcx<double> newton_polish(const double* a, vcx<double> z, int steps) {
-    for (int s = 0; s < steps; ++s) {
-        vcx<double> p0 = cmk<double>(a[P], 0.0), p1 = cmk<double>(0.0, 0.0);
-#pragma unroll
-        for (int j = P - 1; j >= 0; --j) {
-            p1 = cfma(p1, z, p0);
-            p0 = cmk<double>(fma(p0.re, z.re, fma(-p0.im, z.im, a[j])), fma(p0.re, z.im, p0.im * z.re));
-        }
-        const double ns = cnorm_sqr(p1);
-        if (ns == 0.0) break;
-        z = csub(z, cdiv(p0, p1));
     }
     return z;
 }

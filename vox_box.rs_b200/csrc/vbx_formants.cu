@@ -243,19 +243,6 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
     VBX_REQUIRE(ctx, p >= 2 && p <= kMaxRootsOrder, "LPC order for root finding must be in 2..%d", kMaxRootsOrder);
     const int64_t grid = (Q.n_frames + kRootsThreads - 1) / kRootsThreads;
     VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
-    const char* kv = getenv("VBX_ROOTS_KERNEL");
-    if (kv && kv[0] == 'u') {  // the statically unrolled first version, kept for A/B runs
-        static roots_kernel_t tf[kMaxRootsOrder + 1] = {nullptr}, td[kMaxRootsOrder + 1] = {nullptr};
-        static bool filled = false;
-        if (!filled) {
-            fill_f32_lo(tf); fill_f32_hi(tf);
-            fill_f64_lo(td); fill_f64_hi(td);
-            filled = true;
-        }
-        (precision == 1 ? td : tf)[p]<<<(unsigned)grid, 128, 0, ctx->stream>>>(Q);
-        VBX_CHECK_LAUNCH(ctx, "lpc_roots_kernel");
-        return VBX_OK;
-    }
     const bool f32 = (precision != 1);
     const size_t smem = roots_rt_smem_bytes(p, f32);
     if (f32) {

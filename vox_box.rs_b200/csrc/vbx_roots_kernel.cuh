@@ -45,139 +45,13 @@ struct RootsParams {
     int polish_steps;
 };
 
-// Laguerre + deflation for degrees M = P, P−1, …, 3 (statically unrolled so every index is a register).
-template <typename TR, int P, int M, bool FAST> struct SolveAll {
-    static __device__ __forceinline__ void run(vcx<TR>* c, vcx<TR>* roots) {
-        if constexpr (M >= 3) {
-            const vcx<TR> z = laguerre_solve<TR, M, P, FAST>(c, cmk<TR>((TR)-2, (TR)-2));
-            roots[P - M] = z;
-            deflate<TR, M>(c, z);
-            SolveAll<TR, P, M - 1, FAST>::run(c, roots);
-        }
-    }
-};
-
-// One thread per frame.  TR = arithmetic of Laguerre/deflation (float: fast path + fp64 polish;
-// double: the reference's own precision).
-template <int P, typename TR>
-__global__ void __launch_bounds__(128) lpc_roots_kernel(const RootsParams Q) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= Q.n_frames) return;
-    const int R = Q.R;
-    auto write_res = [&](int slot, double fr_, double bw_) {
-        if (Q.out_f64) {
-            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)f * R + slot) * 2;
-            o[0] = fr_; o[1] = bw_;
-        } else {
-            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)f * R + slot) * 2;
-            o[0] = (float)fr_; o[1] = (float)bw_;
-        }
-    };
-    if (Q.status_in && Q.status_in[f] != VBX_OK) {  // the LPC stage failed: find_formants returns Err before root finding
-        if (Q.status_out) Q.status_out[f] = Q.status_in[f];
-        if (Q.nres_out) Q.nres_out[f] = 0;
-        if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
-        return;
-    }
-    // polynomial in ascending powers: a[k] = coefficient of z^k = lpc_{P-k}, a[P] = 1   (lib.rs:78-91)
-    double a[P + 1];
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        const int idx = (P - k) - (Q.lpc_has_one ? 0 : 1);
-        a[k] = Q.lpc_f64 ? reinterpret_cast<const double*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx]
-                         : (double)reinterpret_cast<const float*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx];
-    }
-    a[P] = Q.lpc_has_one ? (Q.lpc_f64 ? reinterpret_cast<const double*>(Q.lpc)[(size_t)f * Q.lpc_stride]
-                                      : (double)reinterpret_cast<const float*>(Q.lpc)[(size_t)f * Q.lpc_stride])
-                         : 1.0;
-    vcx<TR> c[P + 1];
-#pragma unroll
-    for (int k = 0; k <= P; ++k) c[k] = cmk<TR>((TR)a[k], (TR)0);
-    vcx<TR> roots[P];
-    // polynomial.rs:116-128: for m = P down to 3: z = laguerre(coeffs, −2−2i); deflate
-    constexpr bool FAST = (sizeof(TR) == 4);
-    SolveAll<TR, P, P, FAST>::run(c, roots);
-    if (P >= 2) {
-        // polynomial.rs:131-139 quadratic tail: (−c1 ± sqrt(c1² − 4 c2 c0)) / 2c2, "+" first
-        const vcx<TR> a2 = cadd(c[2], c[2]);
-        const vcx<TR> four_ac = cmul(cmul(cmk<TR>((TR)4, (TR)0), c[2]), c[0]);
-        const vcx<TR> d = csqrt_principal(csub(cmul(c[1], c[1]), four_ac));
-        const vcx<TR> x = cneg(c[1]);
-        roots[P - 2] = cdiv(cadd(x, d), a2);
-        roots[P - 1] = cdiv(csub(x, d), a2);
-    } else {
-        roots[0] = cdiv(cneg(c[0]), c[1]);  // polynomial.rs:141-144 linear tail
-    }
-    // resonances: fp64 polish of the roots that can become resonances, then from_root.  The candidates are
-    // compacted first and handled by a real loop (one copy of the polish + atan2/log code, every lane busy):
-    // unrolling this per root made the kernel 250 KB of SASS and instruction-cache bound at scale
-    // (profiles/r1_roots_v0_icache.txt: stall_no_inst 82 %).
-    vcx<double> cz[P];
-    int cidx[P];
-    int nc = 0;
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        const vcx<double> z = cmk<double>((double)roots[k].re, (double)roots[k].im);
-        const bool cand = Q.strict_im ? (z.im > 0.0) : (z.im >= 0.0);
-        if (cand) {
-            cz[nc] = z;
-            cidx[nc] = k;
-            ++nc;
-        } else if (Q.roots_out) {
-            if (Q.out_f64) {
-                double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
-                o[0] = z.re; o[1] = z.im;
-            } else {
-                float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)f * P + k) * 2;
-                o[0] = (float)z.re; o[1] = (float)z.im;
-            }
-        }
-    }
-    double rf[P], rb[P];
-    int cnt = 0;
-#pragma unroll 1
-    for (int j = 0; j < nc; ++j) {
-        vcx<double> z = cz[j];
-        if (Q.polish_steps > 0 && FAST) z = newton_polish<P>(a, z, Q.polish_steps);
-        if (Q.roots_out) {
-            const int k = cidx[j];
-            if (Q.out_f64) {
-                double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
-                o[0] = z.re; o[1] = z.im;
-            } else {
-                float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)f * P + k) * 2;
-                o[0] = (float)z.re; o[1] = (float)z.im;
-            }
-        }
-        double fr_, bw_;
-        if (from_root_f64(z.re, z.im, Q.fs, Q.strict_im != 0, &fr_, &bw_)) {
-            rf[cnt] = fr_;
-            rb[cnt] = bw_;
-            ++cnt;
-        }
-    }
-    if (Q.status_out) Q.status_out[f] = VBX_OK;  // NaN/inf roots yield no resonance, silently, as in the reference
-    if (Q.nres_out) Q.nres_out[f] = cnt;
-    if (Q.res_out) {
-        // stable rank sort by frequency (lib.rs:105-110 / spectrum.rs:207), zero padding behind
-#pragma unroll 1
-        for (int k = 0; k < cnt; ++k) {
-            const double fk = rf[k];
-            int rank = 0;
-#pragma unroll 1
-            for (int j = 0; j < cnt; ++j) rank += (rf[j] < fk || (rf[j] == fk && j < k)) ? 1 : 0;
-            if (rank < R) write_res(rank, fk, rb[k]);
-        }
-        for (int s = cnt; s < R; ++s) write_res(s, 0.0, 0.0);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// Compact variant: runtime loops over the degree, coefficients in shared memory (column layout
-// [k][thread], conflict free), one copy of the Laguerre body.  ~1/10 of the SASS of the statically
-// unrolled kernel above, which is instruction-cache bound once the grid is many waves deep.
-// Same arithmetic in the same order (Horner from the deflated degree M, n = P in the formulas).
+// lpc_roots_rt_kernel: runtime loops over the degree, coefficients in shared memory (column layout
+// [k][thread], conflict free), one copy of the Laguerre body.  The first version of this kernel was
+// statically unrolled over the degree with the polynomial in registers: 250 KB of SASS, instruction-
+// cache bound once the grid was many waves deep (profiles/r1_roots_v0_icache.txt: stall_no_inst 82 %,
+// 76 Mframes/s at the C3 scale against 540 now).  Arithmetic and its order are the reference's (Horner
+// from the deflated degree M, n = P in the formulas).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRootsThreads = 128;
 
@@ -388,18 +262,6 @@ static inline size_t roots_rt_smem_bytes(int P, bool f32) {
     return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)(P + 1) * cs + (size_t)P * cs);
 }
 
-typedef void (*roots_kernel_t)(const RootsParams);
 constexpr int kMaxRootsOrder = 24;
-template <typename TR, int LO, int HI> struct RootsFill {
-    static void fill(roots_kernel_t* t) {
-        t[HI] = lpc_roots_kernel<HI, TR>;
-        if constexpr (HI > LO) RootsFill<TR, LO, HI - 1>::fill(t);
-    }
-};
-// defined in vbx_roots_inst_*.cu
-void fill_f32_lo(roots_kernel_t* t);
-void fill_f32_hi(roots_kernel_t* t);
-void fill_f64_lo(roots_kernel_t* t);
-void fill_f64_hi(roots_kernel_t* t);
 
 }  // namespace vbx_roots
