@@ -227,7 +227,8 @@ VBX_API int64_t vbx_find_formants_real_work_size(int64_t buf_len, int64_t n_coef
 VBX_API int64_t vbx_find_formants_complex_work_size(int64_t n_coeffs);               /* lib.rs:34-36 */
 /* One call = find_formants applied to every frame of the view, in order, inside each segment (utterance):
  * window -> LPC -> roots -> resonances (im > 0, sorted, zero padded to 32) -> estimate_formants.
- * resample_ratio is 1 (the linear resampler of lib.rs:57-61 is not on this path yet).
+ * resample_ratio is 1 here; vbx_find_formants_resampled covers lib.rs:57-61.  With VBX_LPC_BURG the samples may also be
+ * VBX_F64 (so may vbx_lpc_burg's).
  * est_inout [n_segments][n_formants] pairs (state in/out); tracks_out [F][n_formants] (optional);
  * resonances_out [F][32] pairs (optional); nres_out [F] (optional); status_out [F] (optional):
  * VBX_ERR_LPC frames leave the state untouched, exactly as the reference returns Err before the tracker. */
@@ -298,6 +299,17 @@ VBX_API int vbx_normalize(vbx_ctx* ctx, void* x_inout, int32_t dtype, int64_t n_
 /* preemphasis(factor): y[n-1] = x[n-1], y[i] = x[i] + 2π·factor·y[i+1] in place (anti-causal, additive, as written). */
 VBX_API int vbx_preemphasis(vbx_ctx* ctx, void* x_inout, int32_t dtype, int64_t n_signals, int32_t n, int64_t stride,
                             double factor);
+
+/* ---- lib.rs:40-116 find_formants with resample_ratio != 1 (lib.rs:57-61: sample::interpolate::Linear +
+ * Converter::scale_sample_hz) ---------------------------------------------------------------------------------------- */
+/* Every frame of the view (VBX_F32, VBX_I16 or VBX_F64 samples, frames->window = VBX_WINDOW_NONE) is resampled linearly to
+ * ceil(resample_ratio * frame_len) f64 samples, then windowed with the periodic Hann of that length and run through Burg ->
+ * roots -> resonances -> McCandless exactly as vbx_find_formants(.., VBX_LPC_BURG, ..).  sample_rate is passed to
+ * Resonance::from_root unchanged, as the reference does (callers pass the resampled rate).  The reference analyses its whole
+ * `resampled_buf`; here the buffer length equals the resampled length (what tests/lib.rs:31-32 passes).  Device pointers. */
+VBX_API int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
+                                        int32_t n_coeffs, void* est_inout, int32_t n_formants, void* tracks_out,
+                                        void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
 
 #ifdef __cplusplus
 }

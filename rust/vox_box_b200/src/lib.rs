@@ -69,6 +69,13 @@ pub mod ffi {
         pub fn vbx_free(ctx: *mut vbx_ctx, dev: *mut c_void) -> c_int;
         pub fn vbx_memcpy_h2d(ctx: *mut vbx_ctx, dev: *mut c_void, host: *const c_void, bytes: usize) -> c_int;
         pub fn vbx_memcpy_d2h(ctx: *mut vbx_ctx, host: *mut c_void, dev: *const c_void, bytes: usize) -> c_int;
+        pub fn vbx_memcpy_d2d(ctx: *mut vbx_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+        pub fn vbx_mfcc_set_fft_precision(ctx: *mut vbx_ctx, dtype: i32) -> c_int;
+        pub fn vbx_profile_begin(ctx: *mut vbx_ctx) -> c_int;
+        pub fn vbx_profile_end(ctx: *mut vbx_ctx) -> c_int;
+        pub fn vbx_profile_count(ctx: *mut vbx_ctx) -> c_int;
+        pub fn vbx_profile_entry(ctx: *mut vbx_ctx, index: c_int, name_out: *mut c_char, name_len: c_int, ms_total: *mut f64,
+                                 launches: *mut i64) -> c_int;
 
         pub fn vbx_autocorrelate(ctx: *mut vbx_ctx, frames: *const vbx_frames, n_lags: i32, r_out: *mut c_void, out_dtype: i32) -> c_int;
         pub fn vbx_autocorrelate_host(ctx: *mut vbx_ctx, frames: *const vbx_frames, n_lags: i32, r_out: *mut c_void, out_dtype: i32) -> c_int;
@@ -101,6 +108,9 @@ pub mod ffi {
         pub fn vbx_find_formants_host(ctx: *mut vbx_ctx, frames: *const vbx_frames, sample_rate: f64, n_coeffs: i32,
                                       lpc_method: i32, est_inout: *mut c_void, n_formants: i32, tracks_out: *mut c_void,
                                       resonances_out: *mut c_void, nres_out: *mut i32, status_out: *mut u8, dtype: i32) -> c_int;
+        pub fn vbx_find_formants_resampled(ctx: *mut vbx_ctx, frames: *const vbx_frames, sample_rate: f64, resample_ratio: f64,
+                                           n_coeffs: i32, est_inout: *mut c_void, n_formants: i32, tracks_out: *mut c_void,
+                                           resonances_out: *mut c_void, nres_out: *mut i32, status_out: *mut u8, dtype: i32) -> c_int;
         pub fn vbx_pitch(ctx: *mut vbx_ctx, frames: *const vbx_frames, sample_rate: f64, threshold: f64, min_hz: f64, max_hz: f64,
                          max_candidates: i32, cand_out: *mut c_void, n_cand_out: *mut i32, status_out: *mut u8, out_dtype: i32) -> c_int;
         pub fn vbx_pitch_host(ctx: *mut vbx_ctx, frames: *const vbx_frames, sample_rate: f64, threshold: f64, min_hz: f64,

@@ -271,3 +271,44 @@ def test_find_formants_empty_and_bad_args(oracle):
                           16000.0, 12, vb.LPC_BURG, _male()[None])
     assert out["status"].tolist() == [vb.ERR_LPC, vb.ERR_LPC]
     assert np.array_equal(out["tracks"][1], _male())
+
+
+@pytest.mark.parametrize("fs,N,hop,ratio,p", [(44100, 2205, 441, 10000.0 / 44100.0, 13),   # examples/formant_extraction: 50 ms / 10 ms → 10 kHz
+                                               (16000, 400, 160, 1.5, 10),                  # up-sampling
+                                               (16000, 512, 256, 0.5, 8)])
+def test_find_formants_resampled(oracle, fs, N, hop, ratio, p):
+    """lib.rs:57-61: linear resampling inside find_formants (parity vs the oracle's restatement of
+    sample::interpolate::{Linear, Converter}; the reference itself never tests resample_ratio != 1)."""
+    c = ctx()
+    audio = synth.utterance(13, fs, seconds=0.6)
+    F = min(c.n_frames_of(audio.size, N, hop), 24)
+    fs_res = fs * ratio
+    for arr, dt in ((audio, vb.F32), (audio.astype(np.float64), vb.F64)):
+        d = c.to_device(arr)
+        out = c.find_formants_resampled(c.frames(d.ptr, F, N, hop, vb.WINDOW_NONE, dtype=dt), fs_res, ratio, p, _male()[None])
+        state = _male().copy()
+        for f in range(F):
+            o = oracle.find_formants(arr[f * hop: f * hop + N].astype(np.float64), fs_res, p, state, resample_ratio=ratio)
+            assert o["status"] == out["status"][f] == 0
+            state = o["formants"]
+            assert o["n_res"] == out["n_res"][f], f
+            assert np.max(np.abs(out["resonances"][f] - o["resonances"])) < TOL_HZ, f
+            assert np.max(np.abs(out["tracks"][f] - state)) < TOL_HZ, f
+    # ratio 1 takes the plain-copy branch (lib.rs:62-64)
+    d = c.to_device(audio)
+    a = c.find_formants_resampled(c.frames(d.ptr, F, N, hop, vb.WINDOW_NONE), float(fs), 1.0, p, _male()[None])
+    b = c.find_formants(c.frames(d.ptr, F, N, hop, vb.WINDOW_HANN_PERIODIC), float(fs), p, vb.LPC_BURG, _male()[None])
+    assert np.array_equal(a["tracks"], b["tracks"])
+
+
+def test_burg_f64_samples(oracle):
+    """lpc_praat on f64 slices (the reference's own instantiation): VBX_F64 samples, no fp32 rounding of the input."""
+    c = ctx()
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(3 * 300) * np.hanning(900)
+    d = c.to_device(x)
+    co, st = c.lpc_burg(c.frames(d.ptr, 3, 300, 300, vb.WINDOW_NONE, dtype=vb.F64), 10)
+    for f in range(3):
+        s_, ref = oracle.lpc_praat(x[f * 300:(f + 1) * 300], 10)
+        assert s_ == 0 and st.to_host()[f] == 0
+        assert np.max(np.abs(co.to_host()[f] - ref)) < 1e-9 * max(1.0, np.max(np.abs(ref)))

@@ -141,12 +141,13 @@ int vbx_get_window(vbx_ctx* ctx, int kind, int n, const double** dev_out, int sa
     return VBX_OK;
 }
 
-int vbx_check_frames(vbx_ctx* ctx, const vbx_frames* fr) {
+int vbx_check_frames(vbx_ctx* ctx, const vbx_frames* fr, bool allow_f64) {
     VBX_REQUIRE(ctx, fr != nullptr, "frames descriptor is NULL");
     VBX_REQUIRE(ctx, fr->n_frames >= 0, "n_frames < 0");
     VBX_REQUIRE(ctx, fr->frame_len >= 1, "frame_len must be >= 1 (the reference indexes self[0])");
     VBX_REQUIRE(ctx, fr->frame_stride >= 1, "frame_stride must be >= 1");
-    VBX_REQUIRE(ctx, fr->dtype == VBX_F32 || fr->dtype == VBX_I16, "frames dtype must be VBX_F32 or VBX_I16");
+    VBX_REQUIRE(ctx, fr->dtype == VBX_F32 || fr->dtype == VBX_I16 || (allow_f64 && fr->dtype == VBX_F64),
+                allow_f64 ? "frames dtype must be VBX_F32, VBX_I16 or VBX_F64" : "frames dtype must be VBX_F32 or VBX_I16");
     VBX_REQUIRE(ctx, fr->window >= VBX_WINDOW_NONE && fr->window <= VBX_WINDOW_HANN_PERIODIC, "unknown window kind");
     VBX_REQUIRE(ctx, fr->reserved == 0, "frames.reserved must be 0");
     VBX_REQUIRE(ctx, fr->frames_per_segment >= 0, "frames_per_segment < 0");

@@ -14,7 +14,9 @@
 //                         deflation in fp32 (or fp64), fp64 Newton polish on the original polynomial,
 //                         resonances computed and rank-sorted in fp64.
 //   tracker_kernel        one thread per utterance, sequential over its frames (McCandless step).
+#include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "vbx_complex.cuh"
 #include "vbx_internal.cuh"
@@ -54,11 +56,11 @@ __global__ void __launch_bounds__(128) burg_warp_kernel(const BurgParams P) {
     double b1[C], b2[C];
     {
         // xw[j0 .. j0+C] (C+1 values): b1[c] = xw[j0+c], b2[c] = xw[j0+c+1]; entries j >= n−1 are zero
-        double prev = (j0 < n) ? (double)vbx_load_sample<TIn>(x + j0) * __ldg(P.win + j0) : 0.0;
+        double prev = (j0 < n) ? vbx_load_sample_d<TIn>(x + j0) * __ldg(P.win + j0) : 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + c + 1;
-            const double nxt = (j < n) ? (double)vbx_load_sample<TIn>(x + j) * __ldg(P.win + j) : 0.0;
+            const double nxt = (j < n) ? vbx_load_sample_d<TIn>(x + j) * __ldg(P.win + j) : 0.0;
             const bool valid = (j0 + c) < n - 1;
             b1[c] = valid ? prev : 0.0;
             b2[c] = valid ? nxt : 0.0;
@@ -134,8 +136,8 @@ __global__ void __launch_bounds__(256) burg_block_kernel(const BurgParams P, dou
     double* b1 = use_smem ? reinterpret_cast<double*>(smem_raw) : scratch + (size_t)f * 2 * n;
     double* b2 = b1 + n;
     for (int j = tid; j < n - 1; j += T) {
-        b1[j] = (double)vbx_load_sample<TIn>(x + j) * __ldg(P.win + j);
-        b2[j] = (double)vbx_load_sample<TIn>(x + j + 1) * __ldg(P.win + j + 1);
+        b1[j] = vbx_load_sample_d<TIn>(x + j) * __ldg(P.win + j);
+        b2[j] = vbx_load_sample_d<TIn>(x + j + 1) * __ldg(P.win + j + 1);
     }
     if (tid == 0) s_status = VBX_OK;
     __syncthreads();
@@ -779,6 +781,32 @@ __global__ void __launch_bounds__(kTrkThreads) tracker_idx_kernel(const TrackPar
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// lib.rs:57-61 — the linear resampler inside find_formants (sample::interpolate::Linear +
+// Converter::scale_sample_hz): output k interpolates between source samples idx[k] and idx[k]+1 with
+// weight w[k]; (idx, w) follow from the converter's ACCUMULATED interpolation value (interp += 1/ratio,
+// whole frames peeled off while interp >= 1), which depends only on (ratio, k) — so the table is built
+// once on the host, sequentially, exactly as the converter steps, and every frame reuses it.  A source
+// index beyond the frame reads equilibrium (0).  Output: packed [F][rlen] f64 (the reference resamples in
+// S = f64; rounding the resampled frame to fp32 would leak into Burg).
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) resample_kernel(const TIn* __restrict__ base, int64_t n_frames, int64_t stride,
+                                                       int64_t seg_frames, int64_t seg_stride, int n, double scale,
+                                                       const int* __restrict__ idx, const double* __restrict__ w, int rlen,
+                                                       double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_frames * rlen) return;
+    const int64_t f = e / rlen;
+    const int k = (int)(e - f * rlen);
+    const int64_t seg = f / seg_frames;
+    const TIn* x = base + seg * seg_stride + (f - seg * seg_frames) * stride;
+    const int i = __ldg(idx + k);
+    const double left = (i < n) ? vbx_load_sample_d<TIn>(x + i) * scale : 0.0;
+    const double right = (i + 1 < n) ? vbx_load_sample_d<TIn>(x + i + 1) * scale : 0.0;
+    out[e] = left + (right - left) * __ldg(w + k);
+}
+
 int root_precision_default() {
     const char* e = getenv("VBX_ROOTS_F64");
     return (e && e[0] == '1') ? 1 : 0;
@@ -794,7 +822,7 @@ int64_t vbx_find_roots_work_size(int64_t len) { return len * 6 + 4; }           
 
 int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs_out, uint8_t* status_out, int32_t out_dtype) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, frames);
+    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, p >= 1 && p <= 32, "Burg order must be in 1..32");
@@ -804,6 +832,7 @@ int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs
     VBX_REQUIRE(ctx, coeffs_out != nullptr, "coeffs_out is NULL");
     cudaSetDevice(ctx->device);
     if (frames->dtype == VBX_I16) return launch_burg<int16_t>(ctx, frames, p, coeffs_out, status_out, out_dtype);
+    if (frames->dtype == VBX_F64) return launch_burg<double>(ctx, frames, p, coeffs_out, status_out, out_dtype);
     return launch_burg<float>(ctx, frames, p, coeffs_out, status_out, out_dtype);
 }
 
@@ -968,7 +997,7 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
                       void* est_inout, int32_t n_formants, void* tracks_out, void* resonances_out, int32_t* nres_out,
                       uint8_t* status_out, int32_t dtype) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, frames);
+    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/lpc_method == VBX_LPC_BURG);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, lpc_method == VBX_LPC_BURG || lpc_method == VBX_LPC_AUTOCORR, "unknown lpc_method");
@@ -1022,6 +1051,90 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
 }
 
 }  // extern "C"
+
+// lib.rs:40-116 with resample_ratio != 1: resample every frame linearly to ceil(ratio·N) samples (f64), then the
+// reference's own chain — periodic Hann over the resampled length, Burg, roots, resonances, McCandless step.
+// frames->window must be VBX_WINDOW_NONE (find_formants windows AFTER resampling, lib.rs:66-70).
+extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
+                                           int32_t n_coeffs, void* est_inout, int32_t n_formants, void* tracks_out,
+                                           void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/true);
+    if (st != VBX_OK) return st;
+    VBX_REQUIRE(ctx, resample_ratio > 0.0 && resample_ratio <= 64.0, "resample_ratio must be in (0, 64]");
+    VBX_REQUIRE(ctx, frames->window == VBX_WINDOW_NONE, "find_formants windows after resampling: pass VBX_WINDOW_NONE");
+    const int n = frames->frame_len;
+    const int64_t F = frames->n_frames;
+    const double rl = ceil(resample_ratio * (double)n);
+    VBX_REQUIRE(ctx, rl >= 2.0 && rl <= 1.0e6, "resampled frame length out of range");
+    const int rlen = (int)rl;
+    if (F == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    vbx_frames rfr = *frames;
+    if (resample_ratio == 1.0) {  // lib.rs:62-64: plain copy
+        rfr.window = VBX_WINDOW_HANN_PERIODIC;
+        return vbx_find_formants(ctx, &rfr, sample_rate, n_coeffs, VBX_LPC_BURG, est_inout, n_formants, tracks_out, resonances_out,
+                                 nres_out, status_out, dtype);
+    }
+    // the converter's stepping, sequential in f64 (sample 0.10 interpolate::Converter::next)
+    std::vector<int> idx(rlen);
+    std::vector<double> w(rlen);
+    {
+        double interp = 0.0;
+        const double step = 1.0 / resample_ratio;
+        int left = 0;
+        for (int k = 0; k < rlen; ++k) {
+            while (interp >= 1.0) { ++left; interp -= 1.0; }
+            idx[k] = left;
+            w[k] = interp;
+            interp += step;
+        }
+    }
+    // a private block: [F][rlen] f64 + the tables (the inner find_formants uses the context arena)
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t out_bytes = al((size_t)F * rlen * sizeof(double)), idx_bytes = al((size_t)rlen * 4), w_bytes = al((size_t)rlen * 8);
+    void* blk = nullptr;
+    cudaError_t e = cudaMalloc(&blk, out_bytes + idx_bytes + w_bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return vbx_fail(ctx, VBX_ERR_NOMEM, "find_formants_resampled: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    double* d_out = (double*)blk;
+    int* d_idx = (int*)((char*)blk + out_bytes);
+    double* d_w = (double*)((char*)blk + out_bytes + idx_bytes);
+    auto run = [&]() -> int {
+        VBX_CUDA(ctx, cudaMemcpyAsync(d_idx, idx.data(), (size_t)rlen * 4, cudaMemcpyHostToDevice, ctx->stream));
+        VBX_CUDA(ctx, cudaMemcpyAsync(d_w, w.data(), (size_t)rlen * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t total = F * rlen;
+        const int64_t grid = (total + 255) / 256;
+        VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+        const int64_t J = vbx_frames_per_segment(frames);
+        const int64_t seg_stride = frames->frames_per_segment > 0 ? frames->segment_stride : 0;
+        if (frames->dtype == VBX_I16)
+            resample_kernel<int16_t><<<(unsigned)grid, 256, 0, ctx->stream>>>((const int16_t*)frames->base, F, frames->frame_stride, J,
+                                                                           seg_stride, n, 1.0 / 32767.0, d_idx, d_w, rlen, d_out);
+        else if (frames->dtype == VBX_F64)
+            resample_kernel<double><<<(unsigned)grid, 256, 0, ctx->stream>>>((const double*)frames->base, F, frames->frame_stride, J,
+                                                                          seg_stride, n, 1.0, d_idx, d_w, rlen, d_out);
+        else
+            resample_kernel<float><<<(unsigned)grid, 256, 0, ctx->stream>>>((const float*)frames->base, F, frames->frame_stride, J,
+                                                                         seg_stride, n, 1.0, d_idx, d_w, rlen, d_out);
+        VBX_CHECK_LAUNCH(ctx, "resample_kernel");
+        vbx_frames pf;
+        pf.base = d_out; pf.n_frames = F; pf.frame_stride = rlen; pf.frames_per_segment = frames->frames_per_segment;
+        pf.segment_stride = (frames->frames_per_segment > 0) ? frames->frames_per_segment * (int64_t)rlen : 0;
+        pf.frame_len = rlen; pf.dtype = VBX_F64; pf.window = VBX_WINDOW_HANN_PERIODIC; pf.reserved = 0;
+        int s2 = vbx_find_formants(ctx, &pf, sample_rate, n_coeffs, VBX_LPC_BURG, est_inout, n_formants, tracks_out, resonances_out,
+                                   nres_out, status_out, dtype);
+        if (s2 != VBX_OK) return s2;
+        VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the private block is freed on return
+        return VBX_OK;
+    };
+    st = run();
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(blk);
+    return st;
+}
 
 // host twin of vbx_find_formants: chunked H2D / kernels / D2H pipeline over whole utterances (vbx_pipeline.cuh);
 // the tracker state travels once (in before the first chunk, out after the last)

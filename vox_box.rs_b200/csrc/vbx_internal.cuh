@@ -83,7 +83,7 @@ void vbx_window_fill_host(int kind, int n, double* out);
 static inline size_t vbx_dtype_size(int dt) { return dt == VBX_F64 ? 8 : (dt == VBX_I16 ? 2 : 4); }
 
 // validates a vbx_frames descriptor (device or host pointers alike)
-int vbx_check_frames(vbx_ctx* ctx, const vbx_frames* fr);
+int vbx_check_frames(vbx_ctx* ctx, const vbx_frames* fr, bool allow_f64 = false);
 // number of samples spanned by the strided view (0 if n_frames == 0)
 static inline int64_t vbx_frames_per_segment(const vbx_frames* fr) {
     return fr->frames_per_segment > 0 ? fr->frames_per_segment : fr->n_frames;
@@ -104,6 +104,9 @@ template <typename T> __device__ __forceinline__ T vbx_ldg(const T* p) { return 
 template <typename TIn> __device__ __forceinline__ float vbx_load_sample(const TIn* p);
 template <> __device__ __forceinline__ float vbx_load_sample<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float vbx_load_sample<int16_t>(const int16_t* p) { return (float)__ldg(p); }
+// double-valued loader for the paths that also accept f64 samples (Burg / find_formants)
+template <typename TIn> __device__ __forceinline__ double vbx_load_sample_d(const TIn* p) { return (double)vbx_load_sample<TIn>(p); }
+template <> __device__ __forceinline__ double vbx_load_sample_d<double>(const double* p) { return __ldg(p); }
 
 template <typename TOut> __device__ __forceinline__ void vbx_store(TOut* p, double v) { *p = (TOut)v; }
 

@@ -108,6 +108,7 @@ def _declare(L):
     sig("vbx_find_formants", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
     sig("vbx_find_formants_host", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
     _d = C.c_double
+    sig("vbx_find_formants_resampled", C.c_int, _vp, _frp, _d, _d, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
     sig("vbx_pitch", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_pitch_host", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_pitch_extract", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
@@ -575,3 +576,24 @@ Context.rms = lambda self, x: _rows_op(self, "vbx_rms", x)
 Context.max_amplitude = lambda self, x: _rows_op(self, "vbx_max_amplitude", x)
 Context.normalize = _normalize
 Context.preemphasis = _preemphasis
+
+
+def _find_formants_resampled(self, frames, fs, ratio, p, estimates, dtype=F64):
+    """lib.rs:40-116 with resample_ratio != 1 over a device view.  estimates: host [n_segments][k][2]."""
+    F = frames.n_frames
+    J = frames.frames_per_segment or F
+    segs = F // J if J else 0
+    est = np.ascontiguousarray(estimates, dtype=_NP[dtype])
+    k = est.shape[-2]
+    d_est = self.to_device(est.reshape(segs, k, 2))
+    tracks = self.empty((F, k, 2), _NP[dtype])
+    res = self.empty((F, MAX_RESONANCES, 2), _NP[dtype])
+    nres = self.empty((F,), np.int32)
+    st = self.empty((F,), np.uint8)
+    self._check(self.lib.vbx_find_formants_resampled(self.h, C.byref(frames), fs, ratio, p, d_est.ptr, k, tracks.ptr, res.ptr,
+                                                     nres.ptr, st.ptr, dtype), "vbx_find_formants_resampled")
+    return dict(tracks=tracks.to_host(), estimates=d_est.to_host(), resonances=res.to_host(), n_res=nres.to_host(),
+                status=st.to_host())
+
+
+Context.find_formants_resampled = _find_formants_resampled
