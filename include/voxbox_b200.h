@@ -151,6 +151,13 @@ VBX_API int vbx_autocorrelate(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_
 VBX_API int vbx_autocorrelate_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lags, void* r_out,
                                    int32_t out_dtype);
 
+/* periodic.rs:291-304  `impl Autocorrelate for VecDeque<T>` (streaming callers keep the last n samples in a ring):
+ * rings: [n_rings][capacity] of dtype (VBX_F32|VBX_F64); the logical sequence of ring b is x[i] = ring[(heads[b] + i) mod
+ * capacity], i < n (heads == NULL: 0).  No window is applied (the caller's samples are used as they are).
+ * r_out: [n_rings][n_lags], same fold as vbx_autocorrelate (seeded with x[0]), fp64 accumulation. */
+VBX_API int vbx_autocorrelate_ring(vbx_ctx* ctx, const void* rings, int32_t dtype, int64_t n_rings, int64_t capacity,
+                                   const int64_t* heads, int32_t n, int32_t n_lags, void* r_out, int32_t out_dtype);
+
 /* ---- spectrum.rs:50-92  LPC::{lpc_mut, lpc} (Levinson–Durbin) + LPCSolver ---------------- */
 /* r: [F][r_stride] of r_dtype with r_stride >= p+1.  ac_out: [F][p+1] (ac[0] = 1, error-filter
  * sign), kc_out: [F][p] reflection coefficients (may be NULL).  fp64 arithmetic. */

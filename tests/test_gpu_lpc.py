@@ -146,3 +146,21 @@ def test_full_size_properties(oracle):
         seg = flat[u * n_samp + j * hop: u * n_samp + j * hop + N]
         r_ref, a_ref = oracle.batch_lpc(np.ascontiguousarray(seg), 1, N, N, oracle.WIN_HANN_SYMMETRIC, p)
         assert normwise(r[f], r_ref[0]) < 1e-12 and normwise(a[f], a_ref[0]) < TOL
+
+
+def test_autocorrelate_ring_vecdeque(oracle):
+    """periodic.rs:291-304 `impl Autocorrelate for VecDeque`: wrap-around rings give the same lags as the unrolled slice."""
+    c = ctx()
+    rng = np.random.default_rng(8)
+    cap, n = 700, 512
+    rings = rng.standard_normal((5, cap))
+    heads = np.array([0, 1, 188, 350, 699])
+    r = c.autocorrelate_ring(rings, heads, n, 16)
+    for b in range(5):
+        x = np.roll(rings[b], -heads[b])[:n]
+        assert np.max(np.abs(r[b] - oracle.autocorrelate(x, 16))) < 1e-12 * np.max(np.abs(r[b]))
+    r32 = c.autocorrelate_ring(rings.astype(np.float32), heads, n, 16, out_dtype=vb.F32)
+    assert r32.dtype == np.float32 and np.allclose(r32, r, rtol=1e-5)
+    with pytest.raises(vb.VoxBoxError) as e:
+        c.autocorrelate_ring(rings, heads, n, n + 1)
+    assert e.value.status == vb.ERR_BADARG

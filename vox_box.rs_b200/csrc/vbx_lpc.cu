@@ -342,6 +342,41 @@ __global__ void __launch_bounds__(256) autocorr_generic_kernel(const TIn* __rest
     }
 }
 
+// periodic.rs:291-304  `impl Autocorrelate for VecDeque<T>`: the same fold on a ring buffer.  One CTA per ring; the
+// logical sequence x[i] = ring[(head + i) mod capacity] is unrolled into shared memory as f64 when it fits.
+template <typename T>
+__global__ void __launch_bounds__(256) autocorr_ring_kernel(const T* __restrict__ rings, int64_t capacity, const int64_t* __restrict__ heads,
+                                                            int n, int n_lags, void* r_out, int out_f64, int use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_x = reinterpret_cast<double*>(smem_raw);
+    const int64_t b = blockIdx.x;
+    const T* ring = rings + b * capacity;
+    const int64_t head = heads ? heads[b] % capacity : 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    auto at = [&](int i) -> double {
+        int64_t j = head + i;
+        if (j >= capacity) j -= capacity;
+        return (double)ring[j];
+    };
+    if (use_smem) {
+        for (int i = tid; i < n; i += blockDim.x) s_x[i] = at(i);
+        __syncthreads();
+    }
+    auto x = [&](int i) -> double { return use_smem ? s_x[i] : at(i); };
+    const double x0 = x(0);
+    for (int lag = warp; lag < n_lags; lag += nwarps) {
+        double acc = 0.0;
+        for (int i = 1 + lane; i + lag < n; i += 32) acc = fma(x(i), x(i + lag), acc);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += vbx_shfl_xor(acc, m);
+        if (lane == 0) {
+            const double r = x0 + acc;
+            if (out_f64) reinterpret_cast<double*>(r_out)[b * n_lags + lag] = r;
+            else reinterpret_cast<float*>(r_out)[b * n_lags + lag] = (float)r;
+        }
+    }
+}
+
 // Stand-alone Levinson: one thread per frame, r read from global (f32 or f64).
 template <int PORD>
 __global__ void __launch_bounds__(128) levinson_kernel(const void* __restrict__ r_in, int r_f64, int64_t n_frames,
@@ -562,6 +597,33 @@ int vbx_autocorrelate_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t n_lag
     if (ctx && !r_out && frames && frames->n_frames > 0) return vbx_fail(ctx, VBX_ERR_BADARG, "r_out is NULL");
     if (ctx && frames && n_lags < 1) return vbx_fail(ctx, VBX_ERR_BADARG, "n_lags must be >= 1");
     return lpc_host(ctx, frames, n_lags, r_out, nullptr, nullptr, out_dtype, false);
+}
+
+int vbx_autocorrelate_ring(vbx_ctx* ctx, const void* rings, int32_t dtype, int64_t n_rings, int64_t capacity, const int64_t* heads,
+                           int32_t n, int32_t n_lags, void* r_out, int32_t out_dtype) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_rings >= 0 && capacity >= 1, "bad sizes");
+    VBX_REQUIRE(ctx, n >= 1 && n <= capacity, "n must be in 1..capacity (the deque holds n samples)");
+    VBX_REQUIRE(ctx, n_lags >= 1 && n_lags <= n, "n_lags must be in 1..n (`self.len() - lag` underflows in the reference)");
+    if (n_rings == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, rings && r_out, "rings / r_out is NULL");
+    VBX_REQUIRE(ctx, n_rings <= 0x7fffffffLL, "too many rings for one launch");
+    cudaSetDevice(ctx->device);
+    const size_t xs = (size_t)n * sizeof(double);
+    const int use_smem = xs <= ctx->smem_optin ? 1 : 0;
+    if (dtype == VBX_F64) {
+        if (use_smem) VBX_CUDA(ctx, cudaFuncSetAttribute(autocorr_ring_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs));
+        autocorr_ring_kernel<double><<<(unsigned)n_rings, 256, use_smem ? xs : 0, ctx->stream>>>((const double*)rings, capacity, heads, n, n_lags,
+                                                                                          r_out, out_dtype == VBX_F64, use_smem);
+    } else {
+        if (use_smem) VBX_CUDA(ctx, cudaFuncSetAttribute(autocorr_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs));
+        autocorr_ring_kernel<float><<<(unsigned)n_rings, 256, use_smem ? xs : 0, ctx->stream>>>((const float*)rings, capacity, heads, n, n_lags,
+                                                                                         r_out, out_dtype == VBX_F64, use_smem);
+    }
+    VBX_CHECK_LAUNCH(ctx, "autocorr_ring_kernel");
+    return VBX_OK;
 }
 
 int vbx_lpc(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out, int32_t out_dtype) {

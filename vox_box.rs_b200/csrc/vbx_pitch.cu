@@ -475,10 +475,15 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
             const double pl = act ? phil : 0.5, pr = act ? phir : 0.5;
             const double Dd = (double)(D < 0 ? 0 : D);
             const double inv_l = rcp_pos(pl + Dd), inv_r = rcp_pos(pr + Dd);
-            const double s0 = sinpi(pl);
-            double S8l, C8l, S8r, C8r, sl, cl, sr, cr;
-            sincospi(8.0 * inv_l, &S8l, &C8l);
-            sincospi(8.0 * inv_r, &S8r, &C8r);
+            // the three slot-uniform trigonometric values share ONE sincospi call: lane 0 of the slot takes πφ (→ sin πφ),
+            // lane 1 takes 8δ_l, lane 2 takes 8δ_r; five shuffles hand the results to the other lanes of the slot
+            double su, cu;
+            sincospi(l8 == 0 ? pl : (l8 == 1 ? 8.0 * inv_l : (l8 == 2 ? 8.0 * inv_r : 0.0)), &su, &cu);
+            const int sb = lane & 24;
+            const double s0 = __shfl_sync(FULL, su, sb);
+            const double S8l = __shfl_sync(FULL, su, sb + 1), C8l = __shfl_sync(FULL, cu, sb + 1);
+            const double S8r = __shfl_sync(FULL, su, sb + 2), C8r = __shfl_sync(FULL, cu, sb + 2);
+            double sl, cl, sr, cr;
             double tl = pl + (double)l8, tr = pr + (double)l8;
             sincospi(tl * inv_l, &sl, &cl);
             sincospi(tr * inv_r, &sr, &cr);

@@ -91,6 +91,7 @@ def _declare(L):
     sig("vbx_window_table_host", C.c_int, C.c_int, _i32, C.POINTER(C.c_double))
     sig("vbx_autocorrelate", C.c_int, _vp, _frp, _i32, _vp, _i32)
     sig("vbx_autocorrelate_host", C.c_int, _vp, _frp, _i32, _vp, _i32)
+    sig("vbx_autocorrelate_ring", C.c_int, _vp, _vp, _i32, _i64, _i64, _vp, _i32, _i32, _vp, _i32)
     sig("vbx_lpc_levinson", C.c_int, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32)
     sig("vbx_lpc", C.c_int, _vp, _frp, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_lpc_host", C.c_int, _vp, _frp, _i32, _vp, _vp, _vp, _i32)
@@ -597,3 +598,17 @@ def _find_formants_resampled(self, frames, fs, ratio, p, estimates, dtype=F64):
 
 
 Context.find_formants_resampled = _find_formants_resampled
+
+
+def _autocorrelate_ring(self, rings, heads, n, n_lags, out_dtype=F64):
+    """periodic.rs:291-304 Autocorrelate for VecDeque: rings host [B][capacity], heads [B] → r [B][n_lags]."""
+    rings = np.atleast_2d(np.ascontiguousarray(rings))
+    d = self.to_device(rings)
+    h = self.to_device(np.ascontiguousarray(heads, dtype=np.int64))
+    r = self.empty((rings.shape[0], n_lags), _NP[out_dtype])
+    self._check(self.lib.vbx_autocorrelate_ring(self.h, d.ptr, _dt_of(rings), rings.shape[0], rings.shape[1], h.ptr, n, n_lags,
+                                                r.ptr, out_dtype), "vbx_autocorrelate_ring")
+    return r.to_host()
+
+
+Context.autocorrelate_ring = _autocorrelate_ring
