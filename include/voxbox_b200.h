@@ -265,6 +265,16 @@ VBX_API int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample
 /* periodic.rs:320-354 PitchExtractor::next: out[f] = candidates[f][0] (arg-max; the cost fields are unused). */
 VBX_API int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_frames, int32_t max_candidates,
                               void* out);
+/* Opt-in extension (periodic.rs:320-335 declares `PitchExtractor::new(candidates, voiced_unvoiced_cost, voicing_threshold)` and
+ * :394-395 documents the intent, the reference implements arg-max): Boersma's Viterbi path over the candidate lists of vbx_pitch,
+ * sequential inside each segment (utterance).  Maximises sum(local) - sum(transition) with local = strength (- octave_cost *
+ * log2(ceiling_hz / f) for voiced candidates) and transition = 0 (both unvoiced), voiced_unvoiced_cost (one voiced) or
+ * octave_jump_cost * |log2(f1 / f2)| (both voiced).  All three costs 0 reproduces vbx_pitch_extract.  Only the first
+ * min(n_cand[f], max_candidates, 32) candidates of a frame take part (n_cand NULL: max_candidates).
+ * path_out [F] pitch pairs of dtype and/or index_out [F] chosen candidate index. */
+VBX_API int vbx_pitch_viterbi(vbx_ctx* ctx, const void* cand, int32_t dtype, const int32_t* n_cand, int64_t n_segments,
+                              int64_t frames_per_segment, int32_t max_candidates, double voiced_unvoiced_cost,
+                              double octave_jump_cost, double octave_cost, double ceiling_hz, void* path_out, int32_t* index_out);
 /* periodic.rs:29-87 interpolate_sinc(y, offset, nx, x, max_depth), batched: y [n_series][y_len] f64,
  * x [n_series][n_points] f64 -> out [n_series][n_points].  Indices the reference would panic on give NaN. */
 VBX_API int vbx_interpolate_sinc(vbx_ctx* ctx, const double* y, int64_t n_series, int64_t y_len, int64_t offset,

@@ -151,3 +151,59 @@ def test_interpolate_sinc_and_improve_extremum(oracle):
     for i, s in enumerate([float(ixmax + 40), 0.0, float(nx + 2)]):
         ex, ey, _ = oracle.improve_extremum(y, offset, nx, s, interp=oracle.INTERP_PARABOLIC)
         assert abs(xm[0, i] - ex) < 1e-12 and abs(ym[0, i] - ey) < 1e-12
+
+
+def _viterbi_ref(cand, n, vuc, ojc, oc, ceiling):
+    """Plain DP restatement of the path finder (first index wins ties)."""
+    F, K, _ = cand.shape
+    delta, psi = None, np.zeros((F, K), dtype=np.int64)
+    for f in range(F):
+        kc = min(int(n[f]), K, 32)
+        fr, st = cand[f, :kc, 0], cand[f, :kc, 1]
+        v = fr > 0
+        lf = np.where(v, np.log2(np.where(v, fr, 1.0)), 0.0)
+        local = np.where(v, st - oc * (np.log2(ceiling) - lf), st)
+        if f == 0:
+            new = local.copy()
+        else:
+            new = np.empty(kc)
+            for j in range(kc):
+                tr = np.where(v[j] & pv, ojc * np.abs(plf - lf[j]), np.where(v[j] | pv, vuc, 0.0))
+                sc = delta - tr
+                k = int(np.argmax(sc))  # first maximum
+                new[j] = sc[k] + local[j]
+                psi[f, j] = k
+        delta, pv, plf = new, v, lf
+    k = int(np.argmax(delta))
+    idx = np.zeros(F, dtype=np.int64)
+    for f in range(F - 1, -1, -1):
+        idx[f] = k
+        k = psi[f, k]
+    return idx
+
+
+def test_pitch_viterbi_extension():
+    """Opt-in Viterbi path (vbx_pitch_viterbi): equals PitchExtractor's arg-max with zero costs, equals a plain DP otherwise."""
+    c = ctx()
+    fs, N, hop, K = 16000, 640, 160, 16
+    audio = synth.corpus(3, fs, seconds=2.0, first=70)
+    J = c.n_frames_of(audio.shape[1], N, hop)
+    d = c.to_device(audio)
+    fr = c.frames(d.ptr, 3 * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=audio.shape[1])
+    res = c.pitch(fr, float(fs), 0.45, 75.0, 600.0, K)
+    cand, n = res["candidates"].to_host(), res["n_cand"].to_host()
+    path, idx = c.pitch_viterbi(res["candidates"], res["n_cand"], 3, 0.0, 0.0, 0.0, 600.0)
+    assert np.array_equal(idx.to_host(), np.zeros(3 * J, dtype=np.int32))
+    assert np.array_equal(path.to_host(), c.pitch_extract(res["candidates"]).to_host())
+    for vuc, ojc, oc in ((0.14, 0.35, 0.01), (0.5, 1.0, 0.0), (0.02, 0.05, 0.05)):
+        path, idx = c.pitch_viterbi(res["candidates"], res["n_cand"], 3, vuc, ojc, oc, 600.0)
+        got = idx.to_host()
+        for u in range(3):
+            ref = _viterbi_ref(cand[u * J:(u + 1) * J], n[u * J:(u + 1) * J], vuc, ojc, oc, 600.0)
+            assert np.array_equal(got[u * J:(u + 1) * J], ref), (vuc, ojc, oc, u, int(np.count_nonzero(got[u * J:(u + 1) * J] != ref)))
+        p = path.to_host()
+        assert np.array_equal(p[:, 0], cand[np.arange(3 * J), got, 0])
+    # smoother than arg-max: fewer voiced/unvoiced switches with a transition cost
+    sw0 = np.count_nonzero(np.diff((cand[:, 0, 0] > 0).astype(int)))
+    sw1 = np.count_nonzero(np.diff((p[:, 0] > 0).astype(int)))
+    assert sw1 <= sw0

@@ -645,6 +645,86 @@ __global__ void __launch_bounds__(256) pitch_extract_kernel(const T* __restrict_
     out[2 * f + 1] = cand[(size_t)f * max_cand * 2 + 1];
 }
 
+// -------------------------------------------------------------------------------------------
+// Viterbi pitch path (opt-in extension).  The reference declares
+// PitchExtractor::new(candidates, voiced_unvoiced_cost, voicing_threshold) and documents the intent — "a path through
+// these candidates that maximizes both the smoothness of the pitch contour and the strength of the pitches"
+// (periodic.rs:320-335, 394-395) — but implements arg-max.  This is Boersma's (1993) path finder over the candidate
+// lists vbx_pitch returns: maximise Σ_f local(f, k_f) − Σ_f transition(k_{f−1}, k_f) with
+//   local      = strength                                  (unvoiced candidate: its strength = the voicing threshold)
+//                − octave_cost·log2(ceiling / frequency)    (voiced candidates only)
+//   transition = 0 (both unvoiced) | voiced_unvoiced_cost (one voiced) | octave_jump_cost·|log2(f1/f2)| (both voiced).
+// All three costs zero ⇒ the per-frame arg-max, i.e. PitchExtractor as the reference implements it.
+// One warp per utterance: lane j owns candidate j of the current frame, the previous frame's scores travel by shuffle;
+// back-pointers go to a scratch [F][32] byte array; lane 0 backtracks.  Ties keep the lower index.
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) pitch_viterbi_kernel(const T* __restrict__ cand, const int32_t* __restrict__ n_cand, int64_t n_segments,
+                                                            int64_t seg_frames, int K, double vuc, double ojc, double oc, double ceiling,
+                                                            uint8_t* __restrict__ psi, T* __restrict__ path_out, int32_t* __restrict__ index_out) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n_segments) return;
+    const int64_t f0 = u * seg_frames;
+    const double NEG = -1.0e300;
+    double delta = NEG, lf = 0.0;  // best score of a path ending in this lane's candidate; log2 of its frequency
+    bool voiced = false;
+    int kprev = 0;
+    for (int64_t j = 0; j < seg_frames; ++j) {
+        const int64_t f = f0 + j;
+        int kc = n_cand ? n_cand[f] : K;
+        kc = kc < K ? kc : K;
+        kc = kc < 32 ? kc : 32;
+        double freq = 0.0, strength = 0.0;
+        if (lane < kc) {
+            freq = (double)cand[((size_t)f * K + lane) * 2];
+            strength = (double)cand[((size_t)f * K + lane) * 2 + 1];
+        }
+        const bool v = freq > 0.0;
+        const double my_lf = v ? log2(freq) : 0.0;
+        const double local = (lane < kc) ? (v ? strength - oc * (log2(ceiling) - my_lf) : strength) : NEG;
+        double best = (j == 0) ? 0.0 : NEG;
+        int arg = 0;
+        for (int k = 0; k < kprev; ++k) {
+            const double dk = __shfl_sync(FULL, delta, k);
+            const double lk = __shfl_sync(FULL, lf, k);
+            const bool vk = __shfl_sync(FULL, voiced ? 1 : 0, k) != 0;
+            const double tr = (v && vk) ? ojc * fabs(lk - my_lf) : ((v || vk) ? vuc : 0.0);
+            const double sc = dk - tr;
+            if (sc > best) { best = sc; arg = k; }
+        }
+        delta = (lane < kc) ? best + local : NEG;
+        lf = my_lf;
+        voiced = v;
+        kprev = kc;
+        psi[(size_t)f * 32 + lane] = (uint8_t)arg;
+    }
+    if (seg_frames == 0) return;
+    // best final state (lowest index among equals), then backtrack
+    double m = delta;
+    int mi = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(FULL, m, o);
+        const int oi = __shfl_xor_sync(FULL, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int k = mi;
+        for (int64_t j = seg_frames - 1; j >= 0; --j) {
+            const int64_t f = f0 + j;
+            if (index_out) index_out[f] = k;
+            if (path_out) {
+                path_out[2 * f] = cand[((size_t)f * K + k) * 2];
+                path_out[2 * f + 1] = cand[((size_t)f * K + k) * 2 + 1];
+            }
+            k = psi[(size_t)f * 32 + k];
+        }
+    }
+}
+
 constexpr int kMaxPitchFrameLen = 16384;
 
 template <typename TIn>
@@ -793,6 +873,34 @@ int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_f
     else
         pitch_extract_kernel<float><<<(unsigned)grid, 256, 0, ctx->stream>>>((const float*)cand, n_frames, max_candidates, (float*)out);
     VBX_CHECK_LAUNCH(ctx, "pitch_extract_kernel");
+    return VBX_OK;
+}
+
+int vbx_pitch_viterbi(vbx_ctx* ctx, const void* cand, int32_t dtype, const int32_t* n_cand, int64_t n_segments,
+                      int64_t frames_per_segment, int32_t max_candidates, double voiced_unvoiced_cost, double octave_jump_cost,
+                      double octave_cost, double ceiling_hz, void* path_out, int32_t* index_out) {
+    if (!ctx) return VBX_ERR_BADARG;
+    VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
+    VBX_REQUIRE(ctx, n_segments >= 0 && frames_per_segment >= 0, "negative counts");
+    VBX_REQUIRE(ctx, max_candidates >= 1, "max_candidates must be >= 1");
+    VBX_REQUIRE(ctx, ceiling_hz > 0.0, "ceiling_hz must be > 0");
+    const int64_t F = n_segments * frames_per_segment;
+    if (F == 0) return VBX_OK;
+    VBX_REQUIRE(ctx, cand != nullptr && (path_out || index_out), "cand / outputs are NULL");
+    cudaSetDevice(ctx->device);
+    int st = vbx_arena_reserve(ctx, (size_t)F * 32);
+    if (st != VBX_OK) return st;
+    const int64_t grid = (n_segments + 3) / 4;
+    VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
+    if (dtype == VBX_F64)
+        pitch_viterbi_kernel<double><<<(unsigned)grid, 128, 0, ctx->stream>>>((const double*)cand, n_cand, n_segments, frames_per_segment,
+                                                                           max_candidates, voiced_unvoiced_cost, octave_jump_cost, octave_cost,
+                                                                           ceiling_hz, (uint8_t*)ctx->arena, (double*)path_out, index_out);
+    else
+        pitch_viterbi_kernel<float><<<(unsigned)grid, 128, 0, ctx->stream>>>((const float*)cand, n_cand, n_segments, frames_per_segment,
+                                                                          max_candidates, voiced_unvoiced_cost, octave_jump_cost, octave_cost,
+                                                                          ceiling_hz, (uint8_t*)ctx->arena, (float*)path_out, index_out);
+    VBX_CHECK_LAUNCH(ctx, "pitch_viterbi_kernel");
     return VBX_OK;
 }
 

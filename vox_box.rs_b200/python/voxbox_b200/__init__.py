@@ -113,6 +113,7 @@ def _declare(L):
     sig("vbx_pitch", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_pitch_host", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_pitch_extract", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
+    sig("vbx_pitch_viterbi", C.c_int, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _d, _d, _d, _d, _vp, _vp)
     sig("vbx_interpolate_sinc", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp)
     sig("vbx_improve_extremum", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _vp)
     sig("vbx_mfcc", C.c_int, _vp, _frp, _i32, _i32, _d, _d, _d, _vp, _vp, _i32)
@@ -612,3 +613,17 @@ def _autocorrelate_ring(self, rings, heads, n, n_lags, out_dtype=F64):
 
 
 Context.autocorrelate_ring = _autocorrelate_ring
+
+
+def _pitch_viterbi(self, cand, n_cand, n_segments, voiced_unvoiced_cost=0.14, octave_jump_cost=0.35, octave_cost=0.01, ceiling_hz=600.0):
+    """Viterbi path over vbx_pitch's candidate lists (device arrays) → (path [F][2], index [F]) device arrays."""
+    F, K = cand.shape[0], cand.shape[1]
+    path = self.empty((F, 2), cand.dtype)
+    idx = self.empty((F,), np.int32)
+    self._check(self.lib.vbx_pitch_viterbi(self.h, cand.ptr, _dt_of(cand), n_cand.ptr if n_cand is not None else None, n_segments,
+                                           F // n_segments, K, voiced_unvoiced_cost, octave_jump_cost, octave_cost, ceiling_hz,
+                                           path.ptr, idx.ptr), "vbx_pitch_viterbi")
+    return path, idx
+
+
+Context.pitch_viterbi = _pitch_viterbi
