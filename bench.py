@@ -383,22 +383,22 @@ class Workload:
         name -> (pipe that bounds it, flop per frame, HBM bytes per frame, committed ncu summary or None)."""
         cfg, N, hop = self.cfg, self.cfg["n"], self.cfg["hop"]
         p = cfg.get("p", 12)
-        lpc = ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_fused_v1_full.txt")
+        lpc = ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_final_full.txt")
         return {
             "lpc": {"lpc_fused_kernel": lpc},
             "formants": {
-                "lpc_fused_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), None),
+                "lpc_fused_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), "r1_lpc_final_full.txt"),
                 # 10 Laguerre solves x 20 iterations x (3*12 complex FMA*8 + ~60) + polish/resonances ~ 70 k flop (fp32 pipe)
-                "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, None),
-                "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_v0_full.txt"),
+                "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt"),
+                "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_final_full.txt"),
             },
             "pitch": {
-                "pitch_lag_kernel": ("fp32", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, "r1_lag_v0_full.txt"),
+                "pitch_lag_kernel": ("fp32", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, "r1_lag_final_full.txt"),
                 # ~16 candidates x ~26 Brent evaluations x 2(lag+2) terms x ~30 flop (SURVEY §8d C4)
-                "pitch_refine_kernel": ("fp64", 2.5e6, 8 * N, "r1_refine_v1_full.txt"),
+                "pitch_refine_kernel": ("fp64", 2.5e6, 8 * N, "r1_refine_final_full.txt"),
                 "pitch_finalize_kernel": ("fp64", 500.0, 16 * 16 + 140, None),
             },
-            "mfcc": {"mfcc_kernel": ("fp64", 19.5e3, 4 * hop + 4 * 13, "r1_mfcc_v0_full.txt")},
+            "mfcc": {"mfcc_kernel": ("fp64", 19.5e3, 4 * hop + 4 * 13, "r1_mfcc_final_full.txt")},
         }[cfg["kind"]]
 
     def roofline(self, prof, steps, peaks, hbm_peak, hbm_src):
@@ -423,7 +423,10 @@ class Workload:
         k = kernels[dom]
         launches = max(1.0, k["launches_per_step"])
         roof = {"bound": pipe, "achieved": k["tflops"], "peak": peaks[pipe + "_tflops"], "unit": "TFLOP/s", "frac": k["frac"],
-                "traffic": _ncu_traffic(profile) if profile else None, "kernel": dom, "flop_per_frame": flop,
+                "traffic": _ncu_traffic(profile) if profile else None,
+                "traffic_note": f"dram read+write of one ncu --set full capture (profiles/{profile}); that capture's batch may be smaller "
+                                "than this run's — compare per frame" if profile else None,
+                "kernel": dom, "flop_per_frame": flop,
                 "flop_per_launch": flop * self.F / launches, "avg_launch_ms": k["ms_per_step"] / launches, "share_of_step": k["share"],
                 "peak_source": "vbx_measure_peaks: dependent-free FMA loop on this device, this run",
                 "timing": "CUDA events on the library's stream around every launch of the timed region (vbx_profile_begin/end)"}
