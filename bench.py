@@ -385,9 +385,11 @@ class Workload:
         p = cfg.get("p", 12)
         lpc = ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_final_full.txt")
         return {
-            "lpc": {"lpc_fused_kernel": lpc},
+            # lpc_fused16_kernel: the 16-aligned-framing variant (C2, C5 shapes); lpc_fused_kernel: any other framing (C3)
+            "lpc": {"lpc_fused16_kernel": lpc[:3] + ("r1_lpc16_final_full.txt",), "lpc_fused_kernel": lpc},
             "formants": {
                 "lpc_fused_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), "r1_lpc_final_full.txt"),
+                "lpc_fused16_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), "r1_lpc16_final_full.txt"),
                 # 10 Laguerre solves x 20 iterations x (3*12 complex FMA*8 + ~60) + polish/resonances ~ 70 k flop (fp32 pipe)
                 "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt"),
                 "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_final_full.txt"),

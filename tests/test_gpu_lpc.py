@@ -164,3 +164,46 @@ def test_autocorrelate_ring_vecdeque(oracle):
     with pytest.raises(vb.VoxBoxError) as e:
         c.autocorrelate_ring(rings, heads, n, n + 1)
     assert e.value.status == vb.ERR_BADARG
+
+
+@pytest.mark.parametrize("N,hop,n_lags", [(400, 160, 13), (16, 16, 2), (16, 16, 16), (32, 16, 9), (48, 16, 16), (64, 64, 13),
+                                           (512, 128, 11), (512, 512, 16), (400, 480, 13), (1024, 256, 15), (2048, 1024, 14),
+                                           (640, 160, 3)])
+@pytest.mark.parametrize("F", [1, 7, 333])
+def test_autocorrelate_16_aligned_kernel(oracle, N, hop, n_lags, F):
+    """The 16-sample-chunk kernel (frame length and hop multiples of 16, <= 16 lags): odd / even chunk counts (one or two
+    pre-roll chunks for the second half-frame lane), a single chunk, packed and gapped views, partial last CTA, the
+    x[0]-seed quirk (WINDOW_NONE), float and int16 samples, a base pointer that is not 16-byte aligned."""
+    rng = np.random.default_rng(N * 131 + hop * 7 + n_lags)
+    total = (F - 1) * hop + N
+    audio = rng.standard_normal(total + 3).astype(np.float32)
+    c = ctx()
+    d = c.to_device(audio)
+    for off in (0, 3):  # off = 3: staging takes the scalar path
+        for window in (vb.WINDOW_NONE, vb.WINDOW_HANN_SYMMETRIC):
+            r = c.autocorrelate(c.frames(d.ptr + 4 * off, F, N, hop, window), n_lags, out_dtype=vb.F64).to_host()
+            r_ref = oracle.batch_autocorrelate(audio[off:off + total], F, N, hop, window, n_lags)
+            assert np.max(normwise(r, r_ref)) < 1e-12, (off, window)
+    pcm = np.clip(np.round(audio * 8000.0), -32767, 32767).astype(np.int16)
+    dp = c.to_device(pcm)
+    r = c.autocorrelate(c.frames(dp.ptr, F, N, hop, vb.WINDOW_HANN_PERIODIC, dtype=vb.I16), n_lags, out_dtype=vb.F64).to_host()
+    # int16 samples are scaled by 1/32767 on load (folded into the window table): compare with the oracle on the integer
+    # values (exact in fp32) scaled afterwards
+    r_ref = oracle.batch_autocorrelate(pcm[:total].astype(np.float32), F, N, hop, vb.WINDOW_HANN_PERIODIC, n_lags) / 32767.0 ** 2
+    assert np.max(normwise(r, r_ref)) < 1e-12
+
+
+def test_lpc_16_aligned_kernel_segments(oracle):
+    """Segmented batch (utterances) through the 16-aligned kernel: CTAs never straddle segments."""
+    fs, N, hop, p = 16000, 400, 160, 12
+    utts = np.stack([synth.utterance(u, fs, seconds=1.0) for u in range(5)])
+    J = (utts.shape[1] - N) // hop + 1
+    c = ctx()
+    d = c.to_device(utts)
+    fr = c.frames(d.ptr, 5 * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=utts.shape[1])
+    r, ac, kc = c.lpc(fr, p, out_dtype=vb.F64)
+    r, ac = r.to_host(), ac.to_host()
+    for u in range(5):
+        r_ref, ac_ref = oracle.batch_lpc(utts[u], J, N, hop, oracle.WIN_HANN_SYMMETRIC, p)
+        assert np.max(normwise(r[u * J:(u + 1) * J], r_ref)) < 1e-12
+        assert np.max(normwise(ac[u * J:(u + 1) * J], ac_ref)) < 1e-7

@@ -77,6 +77,54 @@ __device__ __forceinline__ void levinson(const double* __restrict__ r, double* _
     for (int i = 0; i <= P; ++i) ac[i] = a[i];
 }
 
+// Common epilogue of the fused kernels: the frame leaders park r in shared memory (the span is dead by
+// then), Levinson runs one thread per frame, and r / ac / kc leave through coalesced stores.
+template <int L>
+__device__ __forceinline__ void lpc_finish(const LpcParams& P, const double (&acc)[L], bool leader, int g, int Gc, int64_t g0,
+                                           double* s_out) {
+    const int tid = threadIdx.x, nthreads = P.threads, G = P.frames_per_cta;
+    __syncthreads();  // everyone is done reading the span; reuse it as output staging
+
+    double* s_r = s_out;                  // [G][L]
+    double* s_ac = s_r + G * L;           // [G][L]
+    double* s_kc = s_ac + G * L;          // [G][L-1]
+    if (leader) {
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) s_r[g * L + lag] = acc[lag];
+    }
+    __syncthreads();
+    if (P.do_levinson && tid < Gc) {
+        double r[L], ac[L], kc[L - 1];
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) r[lag] = s_r[tid * L + lag];
+        levinson<L - 1>(r, ac, kc);
+#pragma unroll
+        for (int lag = 0; lag < L; ++lag) s_ac[tid * L + lag] = ac[lag];
+#pragma unroll
+        for (int j = 0; j < L - 1; ++j) s_kc[tid * (L - 1) + j] = kc[j];
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out --------------------------------------------------------------
+    auto store = [&](void* out, const double* src, int per_frame) {
+        if (!out) return;
+        const int total = Gc * per_frame;
+        const int64_t off = g0 * per_frame;
+        if (P.out_f64) {
+            double* o = reinterpret_cast<double*>(out) + off;
+            for (int idx = tid; idx < total; idx += nthreads) o[idx] = src[idx];
+        } else {
+            float* o = reinterpret_cast<float*>(out) + off;
+            for (int idx = tid; idx < total; idx += nthreads) o[idx] = (float)src[idx];
+        }
+    };
+    store(P.r_out, s_r, L);
+    if (P.do_levinson) {
+        store(P.ac_out, s_ac, L);
+        store(P.kc_out, s_kc, L - 1);
+    }
+}
+
 template <int L, typename TIn>
 __global__ void __launch_bounds__(kMaxThreads, (L <= 13 ? 5 : 1)) lpc_fused_kernel(const LpcParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,47 +315,10 @@ __global__ void __launch_bounds__(kMaxThreads, (L <= 13 ? 5 : 1)) lpc_fused_kern
 #pragma unroll
         for (int lag = 0; lag < L; ++lag) acc[lag] += vbx_shfl_xor(acc[lag], m);
     }
-    __syncthreads();  // everyone is done reading the span; reuse it as output staging
-
-    double* s_r = s_out;                  // [G][L]
-    double* s_ac = s_r + G * L;           // [G][L]
-    double* s_kc = s_ac + G * L;          // [G][L-1]
-    if (g < Gc && q == 0) {
-#pragma unroll
-        for (int lag = 0; lag < L; ++lag) s_r[g * L + lag] = acc[lag];
-    }
-    __syncthreads();
-    if (P.do_levinson && tid < Gc) {
-        double r[L], ac[L], kc[L - 1];
-#pragma unroll
-        for (int lag = 0; lag < L; ++lag) r[lag] = s_r[tid * L + lag];
-        levinson<L - 1>(r, ac, kc);
-#pragma unroll
-        for (int lag = 0; lag < L; ++lag) s_ac[tid * L + lag] = ac[lag];
-#pragma unroll
-        for (int j = 0; j < L - 1; ++j) s_kc[tid * (L - 1) + j] = kc[j];
-    }
-    __syncthreads();
-
-    // ---- coalesced write-out --------------------------------------------------------------
-    auto store = [&](void* out, const double* src, int per_frame) {
-        if (!out) return;
-        const int total = Gc * per_frame;
-        const int64_t off = g0 * per_frame;
-        if (P.out_f64) {
-            double* o = reinterpret_cast<double*>(out) + off;
-            for (int idx = tid; idx < total; idx += nthreads) o[idx] = src[idx];
-        } else {
-            float* o = reinterpret_cast<float*>(out) + off;
-            for (int idx = tid; idx < total; idx += nthreads) o[idx] = (float)src[idx];
-        }
-    };
-    store(P.r_out, s_r, L);
-    if (P.do_levinson) {
-        store(P.ac_out, s_ac, L);
-        store(P.kc_out, s_kc, L - 1);
-    }
+    lpc_finish<L>(P, acc, g < Gc && q == 0, g, Gc, g0, s_out);
 }
+
+#include "vbx_lpc16.cuh"
 
 // Generic fallback (any n_lags / frame length): one CTA per frame, windowed frame as fp64 in
 // shared memory when it fits, lags strided over warps with a shuffle reduction.
@@ -418,6 +429,16 @@ template <typename TIn> struct LpcTable<TIn, 1> {
     static void fill(lpc_kernel_t*) {}
 };
 
+template <typename TIn, int L> struct Lpc16Table {
+    static void fill(lpc_kernel_t* t) {
+        t[L] = lpc_fused16_kernel<L, TIn>;
+        Lpc16Table<TIn, L - 1>::fill(t);
+    }
+};
+template <typename TIn> struct Lpc16Table<TIn, 1> {
+    static void fill(lpc_kernel_t*) {}
+};
+
 typedef void (*lev_kernel_t)(const void*, int, int64_t, int, void*, void*, int);
 template <int P> struct LevTable {
     static void fill(lev_kernel_t* t) {
@@ -478,6 +499,65 @@ bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, 
     return true;
 }
 
+// Plan for lpc_fused16_kernel (vbx_lpc16.cuh): 16-aligned framings with at most 16 lags.  Two lanes per frame;
+// the CTA size is chosen as described in the loop below (C2: 128 threads = 64 frames, 4 CTAs / SM).
+// VBX_LPC16=0 disables the kernel, VBX_LPC16_THREADS=<n> pins the CTA size.
+bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames, int L, LpcParams* P, size_t* smem_bytes) {
+    if (L < 2 || L > kChunk || (n % kChunk) != 0) return false;
+    const int sv = (int)(stride < (int64_t)n ? stride : n);
+    if ((sv % kChunk) != 0) return false;
+    if (const char* e = getenv("VBX_LPC16")) {
+        if (atoi(e) == 0) return false;
+    }
+    const int pad = 4;  // sv / 4 is even, so (sv + 4) / 4 is odd: frame starts walk through all 8 bank groups
+    int force_threads = 0;
+    if (const char* e = getenv("VBX_LPC16_THREADS")) force_threads = atoi(e);
+    const size_t sm_bytes = 228 * 1024, cta_overhead = 1024;
+    int best_threads = 0, best_score = 0;
+    size_t best_bytes = 0;
+    int best_words = 0;
+    for (int threads = 64; threads <= 256; threads += 32) {
+        if (force_threads && threads != force_threads) continue;
+        const int G = threads / 2;
+        const int64_t span = (int64_t)(G - 1) * sv + n;
+        if (span * (int64_t)sv >= (1LL << 32)) continue;
+        const int64_t span_words = span + pad * (span / sv + 1) + 4;
+        const size_t stage_bytes = (size_t)G * (3 * L - 1) * sizeof(double);
+        size_t span_bytes = ((size_t)span_words * sizeof(float) + 15) & ~(size_t)15;
+        const size_t bytes = (size_t)n * sizeof(double) + (span_bytes > stage_bytes ? span_bytes : stage_bytes);
+        if (bytes > ctx->smem_optin) continue;
+        int ctas = (int)(sm_bytes / (bytes + cta_overhead));
+        const int by_regs = 65536 / (96 * threads);
+        if (ctas > by_regs) ctas = by_regs;
+        if (ctas > 32) ctas = 32;
+        // Measured on C2 (profiles/r1_lpc16_cta_sweep.txt): 128 threads with 4 CTAs / SM beats both more, smaller CTAs
+        // (window reload and span overlap per CTA) and fewer, larger ones (coarser waves, more padding frames in an
+        // utterance's last CTA); more than 16 resident warps buys nothing (the kernel is dispatch-bound).  So: reach 16
+        // resident warps with at least 3 CTAs, then prefer the CTA size closest to 128.
+        const int warps = ctas * threads / 32;
+        const int d = threads > 128 ? threads - 128 : 128 - threads;
+        const int score = (warps < 16 ? warps : 16) * 1000 + (ctas >= 3 ? 500 : 0) + (256 - d);
+        (void)seg_frames;
+        if (score > best_score) {
+            best_threads = threads;
+            best_score = score;
+            best_bytes = bytes;
+            best_words = (int)span_words;
+        }
+    }
+    if (!best_threads) return false;
+    P->k = 2;
+    P->threads = best_threads;
+    P->frames_per_cta = best_threads / 2;
+    P->part = 0;
+    P->span_words = best_words;
+    P->sv = sv;
+    P->pad = pad;
+    P->sv_magic = (unsigned)((1ULL << 32) / (unsigned)sv) + 1u;
+    *smem_bytes = best_bytes;
+    return true;
+}
+
 template <typename TIn>
 int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_out, void* kc_out, int out_dtype,
                bool do_levinson) {
@@ -494,7 +574,11 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     LpcParams P;
     memset(&P, 0, sizeof(P));
     size_t smem = 0;
-    const bool fused_ok = (L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem);
+    static lpc_kernel_t table16[kChunk + 1] = {nullptr};
+    if (!table16[2]) Lpc16Table<TIn, kChunk>::fill(table16);
+    const bool fused16 = plan_fused16(ctx, fr->frame_len, fr->frame_stride, vbx_frames_per_segment(fr), L, &P, &smem);
+    const bool fused_ok =
+        fused16 || ((L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem));
     if (fused_ok) {
         P.base = fr->base;
         P.win = win;
@@ -509,12 +593,12 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
         P.n = fr->frame_len;
         P.out_f64 = (out_dtype == VBX_F64);
         P.do_levinson = do_levinson ? 1 : 0;
-        lpc_kernel_t kern = table[L];
+        lpc_kernel_t kern = fused16 ? table16[L] : table[L];
         VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
         kern<<<(unsigned)grid, P.threads, smem, ctx->stream>>>(P);
-        VBX_CHECK_LAUNCH(ctx, "lpc_fused_kernel");
+        VBX_CHECK_LAUNCH(ctx, fused16 ? "lpc_fused16_kernel" : "lpc_fused_kernel");
         return VBX_OK;
     }
 
