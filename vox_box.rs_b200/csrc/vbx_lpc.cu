@@ -510,15 +510,16 @@ bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames,
         if (atoi(e) == 0) return false;
     }
     const int pad = 4;  // sv / 4 is even, so (sv + 4) / 4 is odd: frame starts walk through all 8 bank groups
-    int force_threads = 0;
+    int force_threads = 0, halves = 2;
     if (const char* e = getenv("VBX_LPC16_THREADS")) force_threads = atoi(e);
+    if (const char* e = getenv("VBX_LPC16_K")) halves = atoi(e) == 1 ? 1 : 2;  // lanes per frame (experiments)
     const size_t sm_bytes = 228 * 1024, cta_overhead = 1024;
     int best_threads = 0, best_score = 0;
     size_t best_bytes = 0;
     int best_words = 0;
-    for (int threads = 64; threads <= 256; threads += 32) {
+    for (int threads = 32 * halves; threads <= 256; threads += 32 * halves) {
         if (force_threads && threads != force_threads) continue;
-        const int G = threads / 2;
+        const int G = threads / halves;
         const int64_t span = (int64_t)(G - 1) * sv + n;
         if (span * (int64_t)sv >= (1LL << 32)) continue;
         const int64_t span_words = span + pad * (span / sv + 1) + 4;
@@ -546,9 +547,9 @@ bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames,
         }
     }
     if (!best_threads) return false;
-    P->k = 2;
+    P->k = halves;
     P->threads = best_threads;
-    P->frames_per_cta = best_threads / 2;
+    P->frames_per_cta = best_threads / halves;
     P->part = 0;
     P->span_words = best_words;
     P->sv = sv;

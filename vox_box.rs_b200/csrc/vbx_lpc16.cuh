@@ -7,10 +7,12 @@
 // 16-slot register ring, so that
 //   * samples arrive as 4 LDS.128 and window values as 8 LDS.128 per chunk (0.75 loads per sample instead of 2),
 //   * there is no tail chunk, no pad word inside a chunk (pads are 4 words after every `sv` samples and
-//     sv % 16 == 0) and no separate history loop: the second lane starts one or two chunks early and simply
-//     discards the sums of those pre-roll chunks — its ring then holds the history it needs.
-// The 8 lanes of a quarter-warp (one LDS.128 wavefront) hold 8 consecutive frames of the same half, whose
-// chunk addresses differ by sv + 4 words = an odd number of 16-byte bank groups: conflict-free.
+//     sv % 16 == 0) and no separate history loop: the lane of the second half starts one or two chunks early
+//     and only fills its ring from those pre-roll chunks (window multiply, no lag products).
+// The two halves of a frame live in different warps (even warps: first chunks of 32 frames, odd warps: the
+// rest), so the pre-roll is warp-uniform; the halves meet in shared memory.  The 8 lanes of a quarter-warp (one
+// LDS.128 wavefront) hold 8 consecutive frames, whose chunk addresses differ by sv + 4 words = an odd number of
+// 16-byte bank groups: conflict-free.
 
 constexpr int kChunk = 16;
 
@@ -111,26 +113,42 @@ __global__ void __maxnreg__(96) lpc_fused16_kernel(const LpcParams P) {
     stage_span16<TIn>(P, base, j0, Gc, s_span);
     __syncthreads();
 
-    // lane → (frame, half): quarter-warps hold 8 consecutive frames of one half
-    const int lane = tid & 31;
-    const int q = (lane >> 3) & 1;
-    const int g = (tid >> 5) * 16 + ((lane & 7) | ((lane >> 4) << 3));
+    // warp → (32 frames, half): with two halves per frame (P.k == 2) even warps walk the first chunks of their 32
+    // frames and odd warps the rest, so the pre-roll below is warp-uniform; P.k == 1: a lane walks its whole frame
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q = (P.k == 2) ? (warp & 1) : 0;
+    const int g = ((P.k == 2) ? (warp >> 1) : warp) * 32 + lane;
     double acc[L], h[kChunk];
 #pragma unroll
     for (int j = 0; j < L; ++j) acc[j] = 0.0;
 #pragma unroll
     for (int j = 0; j < kChunk; ++j) h[j] = 0.0;
     if (g < Gc) {
-        const int C = n / kChunk;             // chunks per frame
-        const int nch = (C + 2) >> 1;         // chunk iterations per lane: ceil((C + 1) / 2)
-        const int pre = 2 * nch - C;          // pre-roll chunks of the second half (1 or 2): ring fill only
-        const int cpb = sv / kChunk;          // chunks between pad words
-        int c = q ? C - nch : 0;
+        const int C = n / kChunk;                               // chunks per frame
+        const int nch = (P.k == 2) ? ((C + 2) >> 1) : C;        // chunk passes per lane: ceil((C + 1) / 2)
+        const int pre = q ? 2 * nch - C : 0;                    // pre-roll passes of the second half (1 or 2): ring fill only
+        const int cpb = sv / kChunk;                            // chunks between pad words
+        const int c = q ? C - nch : 0;
         const int blk = c / cpb;
         int left = cpb - (c - blk * cpb);
         const float* sp = s_span + g * (sv + pad) + c * kChunk + pad * blk;
         const double* wp = s_win + c * kChunk;
-        for (int it = 0; it < nch; ++it) {
+        int it = 0;
+        for (; it < pre; ++it) {
+#pragma unroll
+            for (int v = 0; v < kChunk / 4; ++v) {
+                const float4 t = reinterpret_cast<const float4*>(sp)[v];
+                const double2 wa = reinterpret_cast<const double2*>(wp)[2 * v], wb = reinterpret_cast<const double2*>(wp)[2 * v + 1];
+                h[4 * v] = (double)t.x * wa.x;
+                h[4 * v + 1] = (double)t.y * wa.y;
+                h[4 * v + 2] = (double)t.z * wb.x;
+                h[4 * v + 3] = (double)t.w * wb.y;
+            }
+            sp += kChunk;
+            wp += kChunk;
+            if (--left == 0) { sp += pad; left = cpb; }
+        }
+        for (; it < nch; ++it) {
             float xf[kChunk];
 #pragma unroll
             for (int v = 0; v < kChunk / 4; ++v) {
@@ -155,24 +173,29 @@ __global__ void __maxnreg__(96) lpc_fused16_kernel(const LpcParams P) {
             sp += kChunk;
             wp += kChunk;
             if (--left == 0) { sp += pad; left = cpb; }
-            if (it < 2) {
-                if (q == 0) {
-                    if (it == 0) {
-                        // reference quirk (periodic.rs:284): the fold is seeded with x[0] and skips the i = 0
-                        // product, so r[lag] = true_r[lag] − x0·x[lag] + x0; after the first chunk h[j] = xw[j]
-                        const double x0 = h[0];
+            if (it == 0) {
+                // reference quirk (periodic.rs:284): the fold is seeded with x[0] and skips the i = 0 product, so
+                // r[lag] = true_r[lag] − x0·x[lag] + x0; after the first chunk h[j] = xw[j].  (A second-half lane
+                // never gets here: its pre-roll is at least one pass.)
+                const double x0 = h[0];
 #pragma unroll
-                        for (int lag = 0; lag < L; ++lag) acc[lag] = fma(x0, 1.0 - h[lag], acc[lag]);
-                    }
-                } else if (it + 1 == pre) {
-#pragma unroll
-                    for (int lag = 0; lag < L; ++lag) acc[lag] = 0.0;
-                }
+                for (int lag = 0; lag < L; ++lag) acc[lag] = fma(x0, 1.0 - h[lag], acc[lag]);
             }
         }
     }
-    // the two halves of a frame sit 8 lanes apart
+    // second halves park their sums in shared memory (the span is dead after the barrier); first halves add them
+    __syncthreads();
+    double* s_r = s_out;  // [G][L], same layout lpc_finish uses
+    if (q == 1 && g < Gc) {
 #pragma unroll
-    for (int lag = 0; lag < L; ++lag) acc[lag] += vbx_shfl_xor(acc[lag], 8);
+        for (int lag = 0; lag < L; ++lag) s_r[g * L + lag] = acc[lag];
+    }
+    if (P.k == 2) {
+        __syncthreads();
+        if (q == 0 && g < Gc) {
+#pragma unroll
+            for (int lag = 0; lag < L; ++lag) acc[lag] += s_r[g * L + lag];
+        }
+    }
     lpc_finish<L>(P, acc, g < Gc && q == 0, g, Gc, g0, s_out);
 }

@@ -14,6 +14,7 @@
 // Kernel shape: a CTA owns `fpc` frames; every pass spreads the (frame, butterfly)
 // pairs over all threads; the band sums run one thread per (frame, band) in fp64 with host-built
 // f64 slope tables; the DCT one thread per (frame, coefficient) against a host-built f64 cosine table.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -264,6 +265,7 @@ struct MfccTables {
     double2* tw = nullptr;
     double *wu = nullptr, *wd = nullptr, *dct = nullptr;
     int* bins = nullptr;
+    int4* items = nullptr;  // [num_coeffs + 1] intervals between bin edges {j, first bin, end bin, 0}, longest first
     int kmin = 0, kmax = 0;
     int bad = 0;  // a bin the reference would panic on
 };
@@ -335,6 +337,13 @@ int get_tables(vbx_ctx* ctx, int n, int num_coeffs, int n_keep, double f_lo, dou
     if ((st = up(wd.data(), wd.size() * 8, (void**)&t.wd)) != VBX_OK) return st;
     if ((st = up(dct.data(), dct.size() * 8, (void**)&t.dct)) != VBX_OK) return st;
     if ((st = up(bins.data(), bins.size() * 4, (void**)&t.bins)) != VBX_OK) return st;
+    // the intervals between consecutive bin edges, longest first: work items of mfcc_warp_kernel's band stage
+    std::vector<int4> items;
+    if (!t.bad) {
+        for (int j = 0; j <= num_coeffs; ++j) items.push_back(make_int4(j, bins[j], bins[j + 1], 0));
+        std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return a.z - a.y > b.z - b.y; });
+    }
+    if ((st = up(items.data(), items.size() * sizeof(int4), (void**)&t.items)) != VBX_OK) return st;
     cache.push_back(t);
     *out = &cache.back();
     return VBX_OK;
@@ -358,8 +367,10 @@ int launch_fast_one(vbx_ctx* ctx, const mfcc_fast::FastParams& Q) {
     const size_t cs = sizeof(TR) * 2;
     int warps = 4;
     constexpr int WB = FW * MS + ((FW * MS) >> 3) + 1;
+    constexpr int TWN = MS + (R1 - 1) * R0 + (R2 - 1) * R0 * R1 + (R3 - 1) * R0 * R1 * R2;  // mfcc_warp_kernel's twiddle tables
     auto bytes = [&](int w) {
-        return (size_t)N * cs + (size_t)w * WB * cs + ((size_t)Q.n_keep * Q.num_coeffs + 2 * (size_t)N + (size_t)w * FW * Q.num_coeffs) * sizeof(double);
+        return (size_t)TWN * cs + (size_t)w * WB * cs +
+               ((size_t)Q.n_keep * (Q.num_coeffs + 1) + 2 + 2 * (size_t)N + (size_t)w * FW * (2 * Q.num_coeffs + 1)) * sizeof(double);
     };
     while (warps > 1 && bytes(warps) > 56 * 1024) --warps;  // 4 CTAs / SM
     const size_t smem = bytes(warps);
@@ -443,7 +454,8 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
     if (const char* e = getenv("VBX_MFCC_FFT")) f32 = (e[0] == 'f' && e[1] == '3');
     if (P.mode == 0 && !getenv("VBX_MFCC_GENERIC") && P.kmax <= n && num_coeffs <= 128 && n_keep * num_coeffs <= 2048) {
         mfcc_fast::FastParams Q;
-        Q.base = P.base; Q.win = P.win; Q.tw = P.tw; Q.wu = P.wu; Q.wd = P.wd; Q.bins = P.bins; Q.dct = P.dct;
+        Q.base = P.base; Q.win = P.win; Q.tw = P.tw; Q.wu = P.wu; Q.wd = P.wd; Q.bins = P.bins; Q.items = t->items;
+        Q.dct = P.dct;
         Q.out = P.out; Q.energies_out = P.energies_out;
         Q.n_frames = P.n_frames; Q.stride = P.stride; Q.seg_frames = P.seg_frames; Q.seg_stride = P.seg_stride;
         Q.num_coeffs = num_coeffs; Q.n_keep = n_keep; Q.klo = P.klo; Q.khi = P.khi; Q.out_f64 = P.out_f64; Q.warps_per_cta = 0;
@@ -485,7 +497,7 @@ int mfcc_check(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, d
 void vbx_mfcc_cache_free(vbx_ctx* ctx) {
     if (!ctx->mfcc_cache) return;
     for (auto& t : ctx->mfcc_cache->tables) {
-        cudaFree(t.tw); cudaFree(t.wu); cudaFree(t.wd); cudaFree(t.dct); cudaFree(t.bins);
+        cudaFree(t.tw); cudaFree(t.wu); cudaFree(t.wd); cudaFree(t.dct); cudaFree(t.bins); cudaFree(t.items);
     }
     delete ctx->mfcc_cache;
     ctx->mfcc_cache = nullptr;

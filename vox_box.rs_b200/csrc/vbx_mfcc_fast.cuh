@@ -90,11 +90,13 @@ __device__ __forceinline__ void bfly(cxt<TR>* v) {
 // one Stockham pass for FW frames, IN PLACE: every lane first pulls the inputs of all its butterflies into registers
 // (NI = ceil(FW·T/32) butterflies of radix R), the warp synchronises, then everybody writes — so a single
 // shared-memory buffer per warp suffices.  Radix R, LS = product of the earlier radices, rows MS apart.
+// twp = this pass's twiddles laid out [t − 1][k] (t = 1..R−1, k < LS): consecutive lanes read consecutive elements
+// (indexing the exp(−2πik/N) table directly walks it with strides that are multiples of 8 elements: 2- to 8-way
+// bank conflicts, profiles/r1_mfcc_final_full.txt).
 template <typename TR, int MC, int MS, int R, int LS, int FW>
-__device__ __forceinline__ void pass_inplace(cxt<TR>* __restrict__ buf, const cxt<TR>* __restrict__ tw, int lane) {
+__device__ __forceinline__ void pass_inplace(cxt<TR>* __restrict__ buf, const cxt<TR>* __restrict__ twp, int lane) {
     typedef cxt<TR> C;
     constexpr int T = MC / R;
-    constexpr int TWS = (2 * MC) / (LS * R);  // twiddle stride in the exp(−2πi k/N) table, N = 2·MC
     constexpr int NI = (FW * T + 31) / 32;
     C v[NI][R];
 #pragma unroll
@@ -106,7 +108,7 @@ __device__ __forceinline__ void pass_inplace(cxt<TR>* __restrict__ buf, const cx
 #pragma unroll
             for (int t = 0; t < R; ++t) {
                 v[i][t] = buf[pidx(q * MS + j + t * T)];
-                if (t > 0) v[i][t] = cmulf(v[i][t], tw[k * t * TWS]);
+                if (t > 0) v[i][t] = cmulf(v[i][t], twp[(t - 1) * LS + k]);
             }
             bfly<R, TR>(v[i]);
         }
@@ -133,6 +135,7 @@ struct FastParams {
     const double* wu;
     const double* wd;
     const int* bins;
+    const int4* items;    // [num_coeffs + 1] intervals between bin edges {j, first bin, end bin, 0}, longest first
     const double* dct;
     void* out;
     void* energies_out;
@@ -151,19 +154,32 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int M = P.num_coeffs;
-    C* s_tw = reinterpret_cast<C*>(fast_smem);                                   // [N]
+    // twiddles: [MC + 1] of exp(−2πik/N) for the untangle step, then one [R − 1][LS] table per in-place pass
+    constexpr int TW1 = (R1 - 1) * R0, TW2 = (R2 - 1) * R0 * R1, TW3 = (R3 - 1) * R0 * R1 * R2;
+    constexpr int TWN = MS + TW1 + TW2 + TW3;
+    C* s_tw = reinterpret_cast<C*>(fast_smem);                                   // [TWN]
+    C* s_tw1 = s_tw + MS;
+    C* s_tw2 = s_tw1 + TW1;
+    C* s_tw3 = s_tw2 + TW2;
     constexpr int WB = FW * MS + ((FW * MS) >> 3) + 1;                            // padded elements per warp
-    C* buf = s_tw + N + (size_t)warp * WB;                                       // per warp: FW rows of MS (+ padding)
-    double* s_dct = reinterpret_cast<double*>(s_tw + N + (size_t)nwarps * WB);   // [n_keep][M] cosine table (CTA wide)
-    double* s_wu = s_dct + (size_t)P.n_keep * M;                                   // [N] up-slope weights
-    double* s_wd = s_wu + N;                                                       // [N] down-slope weights
-    double* s_e = s_wd + N + (size_t)warp * FW * M;                                // [FW][M]
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const double2 w = __ldg(P.tw + i);
-        s_tw[i] = mk<TR>((TR)w.x, (TR)w.y);
-    }
-    for (int i = threadIdx.x; i < P.n_keep * M; i += blockDim.x) s_dct[i] = __ldg(P.dct + i);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { s_wu[i] = __ldg(P.wu + i); s_wd[i] = __ldg(P.wd + i); }
+    C* buf = s_tw + TWN + (size_t)warp * WB;                                     // per warp: FW rows of MS (+ padding)
+    const int MD = M + 1;                                                          // padded row of the cosine table (bank spread over k)
+    const int ES = 2 * M + 1;                                                      // padded row of the per-frame energies
+    double* s_dct = reinterpret_cast<double*>(s_tw + TWN + (size_t)nwarps * WB);  // [n_keep][M + 1] cosine table (CTA wide)
+    double2* s_w2 = reinterpret_cast<double2*>(                                    // [N] (rising, falling) weight of bin k, 16-byte aligned
+        (reinterpret_cast<uintptr_t>(s_dct + (size_t)P.n_keep * MD) + 15) & ~(uintptr_t)15);
+    double* s_e = reinterpret_cast<double*>(s_w2 + N) + (size_t)warp * FW * ES;    // [FW][2M + 1]: rising | falling half-sums, then energies
+    auto load_tw = [&](int idx) -> C {
+        const double2 w = __ldg(P.tw + idx);
+        return mk<TR>((TR)w.x, (TR)w.y);
+    };
+    for (int i = threadIdx.x; i < MS; i += blockDim.x) s_tw[i] = load_tw(i);
+    for (int i = threadIdx.x; i < TW1; i += blockDim.x) s_tw1[i] = load_tw((i % R0) * (i / R0 + 1) * (N / (R0 * R1)));
+    for (int i = threadIdx.x; i < TW2; i += blockDim.x) s_tw2[i] = load_tw((i % (R0 * R1)) * (i / (R0 * R1) + 1) * (N / (R0 * R1 * R2)));
+    for (int i = threadIdx.x; i < TW3; i += blockDim.x)
+        s_tw3[i] = load_tw((i % (R0 * R1 * R2)) * (i / (R0 * R1 * R2) + 1) * (N / (R0 * R1 * R2 * R3)));
+    for (int i = threadIdx.x; i < P.n_keep * M; i += blockDim.x) s_dct[(i / M) * MD + (i % M)] = __ldg(P.dct + i);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_w2[i] = make_double2(__ldg(P.wu + i), __ldg(P.wd + i));
     __syncthreads();
 
     const int64_t n_groups = (P.n_frames + FW - 1) / FW;
@@ -197,9 +213,9 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
             }
             __syncwarp();
         }
-        if (R1 > 1) pass_inplace<TR, MC, MS, R1, R0, FW>(buf, s_tw, lane);
-        if (R2 > 1) pass_inplace<TR, MC, MS, R2, R0 * R1, FW>(buf, s_tw, lane);
-        if (R3 > 1) pass_inplace<TR, MC, MS, R3, R0 * R1 * R2, FW>(buf, s_tw, lane);
+        if (R1 > 1) pass_inplace<TR, MC, MS, R1, R0, FW>(buf, s_tw1, lane);
+        if (R2 > 1) pass_inplace<TR, MC, MS, R2, R0 * R1, FW>(buf, s_tw2, lane);
+        if (R3 > 1) pass_inplace<TR, MC, MS, R3, R0 * R1 * R2, FW>(buf, s_tw3, lane);
         // ---- untangle the packed transform in place, pairwise (k, MC−k): buf[q][k] = (|X_k|², |X_k|), k = 0..MC --------
         {
             constexpr int H = MC / 2 + 1;  // pairs k = 0..MC/2 (k = MC/2 pairs with itself)
@@ -226,17 +242,32 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
         }
         C* dst = buf;
         // ---- band energies (spectrum.rs:421-435): f64 sums, log10, clamp -------------------------------------------------
+        // The M + 2 bin edges cut the spectrum into M + 1 intervals; interval j is the rising half of band j (power ×
+        // rising weight) and the falling half of band j − 1 (magnitude × the same kind of rising weight — the reference's
+        // quirk).  One lane per (interval, frame) reads every bin once for both sums, each in the reference's order; the
+        // table lists the intervals longest first so that neighbouring lanes loop about equally long.
+#pragma unroll 1
+        for (int item = lane; item < FW * (M + 1); item += 32) {
+            const int it = item / FW, q = item - it * FW;
+            const int4 t = __ldg(P.items + it);
+            const int pk0 = q * MS;
+            double up = 0., down = 0.;
+            for (int k = t.y; k < t.z; ++k) {
+                const C sp = dst[pidx(pk0 + ((2 * k > N) ? N - k : k))];
+                const double2 w = s_w2[k];
+                up = up + (double)sp.x * w.x;
+                down = down + (double)sp.y * w.y;
+            }
+            if (t.x < M) s_e[q * ES + t.x] = up;
+            if (t.x >= 1) s_e[q * ES + M + t.x - 1] = down;
+        }
+        __syncwarp();
 #pragma unroll 1
         for (int item = lane; item < FW * M; item += 32) {
             const int q = item / M, w = item - q * M;
-            const int pk0 = q * MS;
-            const int b0 = __ldg(P.bins + w), b1 = __ldg(P.bins + w + 1), b2 = __ldg(P.bins + w + 2);
-            double up = 0., down = 0.;
-            for (int k = b0; k < b1; ++k) up = up + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].x * s_wu[k];
-            for (int k = b1; k < b2; ++k) down = down + (double)dst[pidx(pk0 + ((2 * k > N) ? N - k : k))].y * s_wd[k];
-            double e = log10(up + down);
+            double e = log10(s_e[q * ES + w] + s_e[q * ES + M + w]);
             e = (e > 1.0e-10) ? e : 1.0e-10;  // f64::max(1e-10): NaN → 1e-10
-            s_e[q * M + w] = e;
+            s_e[q * ES + w] = e;
             if (P.energies_out && q < nf) {
                 const size_t o = (size_t)(f_first + q) * M + w;
                 if (P.out_f64) reinterpret_cast<double*>(P.energies_out)[o] = e;
@@ -244,17 +275,24 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
             }
         }
         __syncwarp();
-        // ---- DCT-II ×2, first n_keep rows (spectrum.rs:391-398) -------------------------------------------------------------
+        // ---- DCT-II ×2, first n_keep rows (spectrum.rs:391-398); four partial sums per row hide the DFMA latency -----------
         const int K = P.n_keep;
 #pragma unroll 1
         for (int item = lane; item < FW * K; item += 32) {
             const int q = item / K, k = item - q * K;
-            const double* e = s_e + q * M;
-            const double* c = s_dct + k * M;
-            double acc = 0.;
-            for (int m = 0; m < M; ++m) acc = acc + e[m] * c[m];
+            const double* e = s_e + q * ES;
+            const double* c = s_dct + k * MD;
+            double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+            int m = 0;
+            for (; m + 4 <= M; m += 4) {
+                a0 = fma(e[m], c[m], a0);
+                a1 = fma(e[m + 1], c[m + 1], a1);
+                a2 = fma(e[m + 2], c[m + 2], a2);
+                a3 = fma(e[m + 3], c[m + 3], a3);
+            }
+            for (; m < M; ++m) a0 = fma(e[m], c[m], a0);
             if (q < nf) {
-                const double v = 2. * acc;
+                const double v = 2. * ((a0 + a1) + (a2 + a3));
                 const size_t o = (size_t)(f_first + q) * K + k;
                 if (P.out_f64) reinterpret_cast<double*>(P.out)[o] = v;
                 else reinterpret_cast<float*>(P.out)[o] = (float)v;
