@@ -402,17 +402,15 @@ __global__ void __launch_bounds__(256) pitch_refine_kernel(const PitchParams P) 
 // and run Brent in lockstep; the term loop runs to the largest D of the four, shorter slots are masked.
 // Brent's state is replicated in the 8 lanes of a slot (identical arithmetic ⇒ identical values), the only
 // cross-lane traffic is the 3-step butterfly that sums the 8 partial sums.
-__device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positive x: MUFU seed + 2 Newton steps
+__device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positive x: MUFU seed + one third-order step
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);   // seed error, <= 1e-6 relative (tools/cuda/rcp_test.cu)
+    return fma(r, fma(e, e, e), r);     // r·(1 + e + e²): error e³, i.e. below one ulp
 }
 
-// (A single Newton step would leave 1e-12 relative error — tools/cuda/rcp_test.cu — and that already moves some weak
-// candidates' Brent paths by > 0.1 Hz in tests/test_gpu_pitch.py, so the reciprocal keeps both steps.)
+// (A single Newton step would leave 1e-12 relative error and that already moves some weak candidates' Brent paths by
+// > 0.1 Hz in tests/test_gpu_pitch.py; the third-order step costs the same three DFMAs as one-and-a-half Newton steps.)
 __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
@@ -495,20 +493,41 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
             const int L = offset + nr, R = offset + nl;
             const int Dmax = __reduce_max_sync(FULL, D);
             double acc = 0.;
-            for (int n = l8; n <= Dmax; n += 8) {
-                const bool on = (n <= D);
-                int il = L - n;
-                il = il < 0 ? 0 : il;
-                int ir = R + n;
-                ir = ir < 0 ? 0 : ir;
-                const double yl = (on && il < N) ? __ldg(y + il) : 0.0;
-                const double yr = (on && ir < N) ? __ldg(y + ir) : 0.0;
-                const double num = fma(yl * hl, tr, (yr * hr) * tl);
-                acc = fma(num, rcp_pos(tl * tr), acc);
-                // advance: t += 8, Hann factors one recurrence step
-                const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
-                hlp = hl; hl = nhl; hrp = hr; hr = nhr;
-                tl += 8.0; tr += 8.0;
+            // Left terms read y[L − n] (>= 0 because D <= L), right terms y[R + n]; beyond N the zero extension
+            // contributes nothing.  When every active slot has 0 <= R and L < N (always, for candidates at positive
+            // lags) the bounds collapse into one per-side depth and the loads walk two pointers.
+            const bool plain = !act || (R >= 0 && L < N);
+            if (__all_sync(FULL, plain)) {
+                const int Dl = D, Dr = min(D, N - 1 - R);
+                const double* __restrict__ ql = y + (act ? L - l8 : 0);
+                const double* __restrict__ qr = y + (act ? R + l8 : 0);
+                for (int n = l8; n <= Dmax; n += 8) {
+                    const double yl = (n <= Dl) ? __ldg(ql) : 0.0;
+                    const double yr = (n <= Dr) ? __ldg(qr) : 0.0;
+                    ql -= 8;
+                    qr += 8;
+                    const double num = fma(yl * hl, tr, (yr * hr) * tl);
+                    acc = fma(num, rcp_pos(tl * tr), acc);
+                    const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
+                    hlp = hl; hl = nhl; hrp = hr; hr = nhr;
+                    tl += 8.0; tr += 8.0;
+                }
+            } else {
+                for (int n = l8; n <= Dmax; n += 8) {
+                    const bool on = (n <= D);
+                    int il = L - n;
+                    il = il < 0 ? 0 : il;
+                    int ir = R + n;
+                    ir = ir < 0 ? 0 : ir;
+                    const double yl = (on && il < N) ? __ldg(y + il) : 0.0;
+                    const double yr = (on && ir < N) ? __ldg(y + ir) : 0.0;
+                    const double num = fma(yl * hl, tr, (yr * hr) * tl);
+                    acc = fma(num, rcp_pos(tl * tr), acc);
+                    // advance: t += 8, Hann factors one recurrence step
+                    const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
+                    hlp = hl; hl = nhl; hrp = hr; hr = nhr;
+                    tl += 8.0; tr += 8.0;
+                }
             }
             acc *= sgn;
             acc += __shfl_xor_sync(FULL, acc, 1);
