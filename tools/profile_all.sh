@@ -10,7 +10,8 @@ full() { # name regex command...
   local name=$1 rx=$2; shift 2
   ncu --set full --clock-control none --import-source on -k regex:$rx -c 1 -o gpurun_out/prof_${name}_final "$@" > gpurun_out/ncu_${name}_final.log 2>&1
 }
-full lpc lpc_fused python bench.py --config c2 --steps 1 --warmup 0 --no-cpu
+full lpc16 lpc_fused16 python bench.py --config c2 --steps 1 --warmup 0 --no-cpu
+full lpc "lpc_fused_kernel" python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
 full roots lpc_roots_rt python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
 full tracker tracker_idx python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
 full lag pitch_lag python bench.py --config c4 --utts 48 --steps 1 --warmup 0 --no-cpu
