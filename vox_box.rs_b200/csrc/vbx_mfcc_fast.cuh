@@ -225,16 +225,15 @@ __global__ void __launch_bounds__(128, 4) mfcc_warp_kernel(const FastParams P) {
                 const int zb0 = q * MS;
                 const int k2 = MC - k;
                 const C za = buf[pidx(zb0 + k)], zb = buf[pidx(zb0 + (k2 == MC ? 0 : k2))];
-                auto spec = [&](C zk, C zc, int kk) -> C {
-                    const C zm = mk<TR>(zc.x, -zc.y);
-                    const C E = mk<TR>((TR)0.5 * (zk.x + zm.x), (TR)0.5 * (zk.y + zm.y));
-                    const C O = mk<TR>((TR)0.5 * (zk.x - zm.x), (TR)0.5 * (zk.y - zm.y));
-                    const C X = caddf(E, mulnegi(cmulf(s_tw[kk], O)));
-                    const TR pw = X.x * X.x + X.y * X.y;
-                    return mk<TR>(pw, sqrt(pw));
-                };
-                const C pa = spec(za, zb, k);     // X_k     from Z_k and conj(Z_{MC−k})
-                const C pb = spec(zb, za, k2);    // X_{MC−k} from Z_{MC−k} and conj(Z_k)   (k = 0: the Nyquist bin X_MC)
+                // X_k = E − i·T and X_{MC−k} = conj(E) − i·conj(T) with E = (Z_k + conj Z_{MC−k})/2, O = (Z_k − conj Z_{MC−k})/2,
+                // T = W_N^k·O  (W_N^{MC−k} = −conj W_N^k, and the pair's even / odd parts are conjugates of each other)
+                const C E = mk<TR>((TR)0.5 * (za.x + zb.x), (TR)0.5 * (za.y - zb.y));
+                const C O = mk<TR>((TR)0.5 * (za.x - zb.x), (TR)0.5 * (za.y + zb.y));
+                const C T = cmulf(s_tw[k], O);
+                const TR xr = E.x + T.y, xi = E.y - T.x;      // X_k
+                const TR yr = E.x - T.y, yi = -E.y - T.x;     // X_{MC−k}   (k = 0: the Nyquist bin X_MC)
+                const TR pwa = xr * xr + xi * xi, pwb = yr * yr + yi * yi;
+                const C pa = mk<TR>(pwa, sqrt(pwa)), pb = mk<TR>(pwb, sqrt(pwb));
                 buf[pidx(zb0 + k)] = pa;
                 buf[pidx(zb0 + k2)] = pb;
             }
