@@ -411,14 +411,20 @@ __device__ __forceinline__ double rcp_pos(double x) {  // 1/x for normal positiv
 
 // (A single Newton step would leave 1e-12 relative error and that already moves some weak candidates' Brent paths by
 // > 0.1 Hz in tests/test_gpu_pitch.py; the third-order step costs the same three DFMAs as one-and-a-half Newton steps.)
+constexpr int kRefineTile = 256;
+
 __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
-    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long total = (long long)*P.counter;
-    const long long n_groups = (total + 3) >> 2;
     const int N = P.n;
+    // A CTA takes tiles of kRefineTile consecutive work-list entries (about ten frames) and walks each tile in order of
+    // the start abscissa, i.e. of the interpolation depth D: the four slots of a warp then run term loops of nearly the
+    // same length (the list order — ascending lag inside a frame — leaves 19 % of the lanes of the term loop idle, a
+    // sorted tile 3 %).  Results do not depend on the grouping: every slot's arithmetic is its own.
+    __shared__ float s_key[kRefineTile];
+    __shared__ unsigned short s_ord[kRefineTile];
     const int offset = -P.ixmax - 1;
     const int nx = P.ixmax - offset;
     const int ylen = 2 * N;
@@ -427,9 +433,25 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
     const double sgn = (l8 & 1) ? -1.0 : 1.0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    for (long long g = warp_global; g < n_groups; g += n_warps) {
-        const long long e = 4 * g + sub;
-        const bool valid = e < total;
+    for (long long tile0 = (long long)blockIdx.x * kRefineTile; tile0 < total; tile0 += (long long)gridDim.x * kRefineTile) {
+    const int tcnt = (int)min((long long)kRefineTile, total - tile0);
+    __syncthreads();  // the previous tile's order is no longer read
+    for (int i = threadIdx.x; i < tcnt; i += blockDim.x) s_key[i] = (float)P.list[tile0 + i].n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tcnt; i += blockDim.x) {
+        const float ki = s_key[i];
+        int rank = 0;
+        for (int j = 0; j < tcnt; ++j) {
+            const float kj = s_key[j];
+            rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        }
+        s_ord[rank] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int g = warp; 4 * g < tcnt; g += nwarps) {
+        const int slot = 4 * g + sub;
+        const bool valid = slot < tcnt;
+        const long long e = tile0 + (valid ? (int)s_ord[slot] : 0);
         PitchCand cd;
         cd.frame = 0; cd.k = 0; cd.n = 0.0;
         if (valid) cd = P.list[e];
@@ -585,6 +607,238 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
             if (ymid > 1.) ymid = 1. / ymid;
             P.refined[e] = make_double2(P.fs / xmid, ymid);
         }
+    }
+    }
+}
+
+// K7 (v2): the same slots, fed from a queue.  Brent needs a different number of evaluations for every candidate (about
+// 12 to 40), so in the lockstep version above a warp idles a finished slot until the slowest of its four is done.  Here
+// every slot draws its next candidate from the tile's sorted order (a shared-memory cursor) as soon as it finishes:
+// the warp stays in lockstep only over single evaluations of the interpolant.
+__global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, l8 = lane & 7;
+    const long long total = (long long)*P.counter;
+    const int N = P.n;
+    // A CTA takes tiles of kRefineTile consecutive work-list entries (about ten frames) and walks each tile in order of
+    // the start abscissa, i.e. of the interpolation depth D: the four slots of a warp then run term loops of nearly the
+    // same length (the list order — ascending lag inside a frame — leaves 19 % of the lanes of the term loop idle, a
+    // sorted tile 3 %).  Results do not depend on the grouping: every slot's arithmetic is its own.
+    __shared__ float s_key[kRefineTile];
+    __shared__ unsigned short s_ord[kRefineTile];
+    __shared__ int s_next;
+    const int offset = -P.ixmax - 1;
+    const int nx = P.ixmax - offset;
+    const int ylen = 2 * N;
+    const double golden = 1. - 0.6180339887498948482045868343656381177203091798057628621;
+    const double EPS = 2.220446049250313e-16, sqrt_epsilon = 1.4901161193847656e-08, tol = 1e-10;
+    const double sgn = (l8 & 1) ? -1.0 : 1.0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (long long tile0 = (long long)blockIdx.x * kRefineTile; tile0 < total; tile0 += (long long)gridDim.x * kRefineTile) {
+    const int tcnt = (int)min((long long)kRefineTile, total - tile0);
+    __syncthreads();  // the previous tile's order is no longer read
+    if (threadIdx.x == 0) s_next = 0;
+    for (int i = threadIdx.x; i < tcnt; i += blockDim.x) s_key[i] = (float)P.list[tile0 + i].n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tcnt; i += blockDim.x) {
+        const float ki = s_key[i];
+        int rank = 0;
+        for (int j = 0; j < tcnt; ++j) {
+            const float kj = s_key[j];
+            rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        }
+        s_ord[rank] = (unsigned short)i;
+    }
+    __syncthreads();
+    // slot state (replicated in the 8 lanes of a slot)
+    bool have = false, dry = false;     // have: a candidate is being refined; dry: the tile's queue is exhausted
+    long long e = 0;
+    const double* __restrict__ y = P.y;
+    double rx = 0., ry = 0.;
+    double a = 0., b = 0., v = 0., w = 0., x = 0., fv = 0., fw = 0., fx = 0., t = 0.;
+    int iter = 0;
+    auto yat = [&](int idx) -> double { return (idx >= 0 && idx < N) ? __ldg(y + idx) : 0.0; };  // zero-extended to 2N
+    {
+        while (true) {
+            // ---- free slots draw the next candidate of the tile ---------------------------------------------------------
+            const bool want = !have && !dry;
+            int qi = -1;
+            if (want && l8 == 0) qi = atomicAdd(&s_next, 1);
+            qi = __shfl_sync(FULL, qi, lane & 24);
+            if (want) {
+                if (qi >= tcnt) {
+                    dry = true;
+                } else {
+                    e = tile0 + (int)s_ord[qi];
+                    const PitchCand cd = P.list[e];
+                    y = P.y + (size_t)cd.frame * N;
+                    const double ixmid = cd.n;
+                    // improve_extremum's early returns (periodic.rs:193-194)
+                    if (ixmid == 0. || ixmid >= (double)nx) {
+                        if (l8 == 0) {
+                            double ymid = (ixmid == 0.) ? yat(0) : yat(nx - 1);
+                            const double xmid = ((ixmid == 0.) ? 0. : (double)nx) + (double)offset;
+                            if (ymid > 1.) ymid = 1. / ymid;
+                            P.refined[e] = make_double2(P.fs / xmid, ymid);
+                        }
+                    } else {
+                        // brent_maximize(f, (ixmid−1, ixmid+1), tol = 1e-10)
+                        a = ixmid - 1.; b = ixmid + 1.;
+                        v = a + golden * (b - a); w = v; x = v; fv = 0.; fw = 0.; fx = 0.;
+                        t = v;
+                        iter = 0;  // 0: the initial evaluation is pending
+                        have = true;
+                    }
+                }
+            }
+            if (!__any_sync(FULL, have)) {
+                if (__all_sync(FULL, dry)) break;
+                continue;
+            }
+            bool done = !have;
+        {
+            // ---- interpolate_sinc(y, offset, nx, t, 1200): per-slot setup ----------------------------------------
+            const double fl = floor(t);
+            const int nl = (fl > 0.0) ? (int)fmin(fl, 1.0e9) : 0;
+            const int nr = nl + 1;
+            const double phil = t - (double)nl, phir = 1. - phil;
+            bool special = done;
+            double sval = 0.;
+            int D = -1;
+            if (!done) {
+                if (t > (double)nx) { special = true; const int i = offset + nx - 1; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else if (t < 0.) { special = true; sval = yat(0); }
+                else if (fabs(t - (double)nl) < 1.0e-10) { special = true; const int i = offset + nl; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else if (fabs(t - (double)nr) < 1.0e-10) { special = true; const int i = offset + nr; sval = (i < 0 || i >= ylen) ? qnan : yat(i); }
+                else {
+                    int md = 1200;
+                    if (offset + nr < md) md = (offset + nr < 0) ? 0 : offset + nr;
+                    if (offset + nl + md >= nx) md = nx - offset + nl - 1;
+                    D = md;
+                }
+            }
+            const bool act = !special;
+            const double pl = act ? phil : 0.5, pr = act ? phir : 0.5;
+            const double Dd = (double)(D < 0 ? 0 : D);
+            const double inv_l = rcp_pos(pl + Dd), inv_r = rcp_pos(pr + Dd);
+            // the three slot-uniform trigonometric values share ONE sincospi call: lane 0 of the slot takes πφ (→ sin πφ),
+            // lane 1 takes 8δ_l, lane 2 takes 8δ_r; five shuffles hand the results to the other lanes of the slot
+            double su, cu;
+            sincospi(l8 == 0 ? pl : (l8 == 1 ? 8.0 * inv_l : (l8 == 2 ? 8.0 * inv_r : 0.0)), &su, &cu);
+            const int sb = lane & 24;
+            const double s0 = __shfl_sync(FULL, su, sb);
+            const double S8l = __shfl_sync(FULL, su, sb + 1), C8l = __shfl_sync(FULL, cu, sb + 1);
+            const double S8r = __shfl_sync(FULL, su, sb + 2), C8r = __shfl_sync(FULL, cu, sb + 2);
+            double sl, cl, sr, cr;
+            double tl = pl + (double)l8, tr = pr + (double)l8;
+            sincospi(tl * inv_l, &sl, &cl);
+            sincospi(tr * inv_r, &sr, &cr);
+            // Hann factor h_j = ½ + ½cos(θ0 + 8δ·j) by the three-term recurrence h_{j+1} = K·h_j − h_{j−1} + (1 − K/2),
+            // K = 2cos 8δ (error growth ~j²·ε, j <= 150), started from h_0 and h_{−1} = ½ + ½cos(θ0 − 8δ)
+            double hl = fma(0.5, cl, 0.5), hlp = fma(0.5, fma(cl, C8l, sl * S8l), 0.5);
+            double hr = fma(0.5, cr, 0.5), hrp = fma(0.5, fma(cr, C8r, sr * S8r), 0.5);
+            const double Kl = 2.0 * C8l, Kr = 2.0 * C8r, Cl = 1.0 - C8l, Cr = 1.0 - C8r;
+            const int L = offset + nr, R = offset + nl;
+            const int Dmax = __reduce_max_sync(FULL, D);
+            double acc = 0.;
+            // Left terms read y[L − n] (>= 0 because D <= L), right terms y[R + n]; beyond N the zero extension
+            // contributes nothing.  When every active slot has 0 <= R and L < N (always, for candidates at positive
+            // lags) the bounds collapse into one per-side depth and the loads walk two pointers.
+            const bool plain = !act || (R >= 0 && L < N);
+            if (__all_sync(FULL, plain)) {
+                const int Dl = D, Dr = min(D, N - 1 - R);
+                const double* __restrict__ ql = y + (act ? L - l8 : 0);
+                const double* __restrict__ qr = y + (act ? R + l8 : 0);
+                for (int n = l8; n <= Dmax; n += 8) {
+                    const double yl = (n <= Dl) ? __ldg(ql) : 0.0;
+                    const double yr = (n <= Dr) ? __ldg(qr) : 0.0;
+                    ql -= 8;
+                    qr += 8;
+                    const double num = fma(yl * hl, tr, (yr * hr) * tl);
+                    acc = fma(num, rcp_pos(tl * tr), acc);
+                    const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
+                    hlp = hl; hl = nhl; hrp = hr; hr = nhr;
+                    tl += 8.0; tr += 8.0;
+                }
+            } else {
+                for (int n = l8; n <= Dmax; n += 8) {
+                    const bool on = (n <= D);
+                    int il = L - n;
+                    il = il < 0 ? 0 : il;
+                    int ir = R + n;
+                    ir = ir < 0 ? 0 : ir;
+                    const double yl = (on && il < N) ? __ldg(y + il) : 0.0;
+                    const double yr = (on && ir < N) ? __ldg(y + ir) : 0.0;
+                    const double num = fma(yl * hl, tr, (yr * hr) * tl);
+                    acc = fma(num, rcp_pos(tl * tr), acc);
+                    // advance: t += 8, Hann factors one recurrence step
+                    const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
+                    hlp = hl; hl = nhl; hrp = hr; hr = nhr;
+                    tl += 8.0; tr += 8.0;
+                }
+            }
+            acc *= sgn;
+            acc += __shfl_xor_sync(FULL, acc, 1);
+            acc += __shfl_xor_sync(FULL, acc, 2);
+            acc += __shfl_xor_sync(FULL, acc, 4);
+            const double ft = special ? sval : acc * (s0 * (1.0 / kPi));
+            // ---- Brent update (periodic.rs:121-186) ---------------------------------------------------------------------
+            if (!done) {
+                if (iter == 0) {
+                    fv = ft; fx = ft; fw = ft;
+                    iter = 1;
+                } else {
+                    if (ft <= fx) {
+                        if (t < x) b = x; else a = x;
+                        v = w; w = x; x = t;
+                        fv = fw; fw = fx; fx = ft;
+                    } else {
+                        if (t < x) a = t; else b = t;
+                        if (ft <= fw || fabs(w - x) < EPS) {
+                            v = w; w = t;
+                            fv = fw; fw = ft;
+                        } else if (ft <= fv || fabs(v - x) < EPS || fabs(v - w) < EPS) {
+                            v = t;
+                            fv = ft;
+                        }
+                    }
+                    ++iter;
+                }
+                if (iter > 60) {
+                    done = true; rx = x; ry = fx;
+                } else {
+                    const double range = b - a, middle_range = (a + b) * 0.5;
+                    const double tol_act = sqrt_epsilon * fabs(x) + tol / 3.;
+                    if (fabs(x - middle_range) + range * 0.5 <= 2. * tol_act) {
+                        done = true; rx = x; ry = fx;
+                    } else {
+                        double new_step = (x < middle_range) ? golden * (b - x) : golden * (a - x);
+                        if (fabs(x - w) >= tol_act) {
+                            const double tt = (x - w) * (fx - fv);
+                            double q = (x - v) * (fx - fw);
+                            double p = (x - v) * q - (x - w) * tt;
+                            q = 2. * q - tt;
+                            if (q > 0.) p = -p; else q = -q;
+                            if (fabs(p) < fabs(new_step * q) && p > q * (a - x + 2. * tol_act) && p < q * (b - x - 2. * tol_act))
+                                new_step = p / q;
+                        }
+                        if (fabs(new_step) < tol_act) new_step = (new_step > 0.) ? tol_act : -tol_act;
+                        t = x + new_step;
+                    }
+                }
+            }
+        }
+            if (have && done) {
+                if (l8 == 0) {
+                    double xmid = rx + (double)offset, ymid = ry;
+                    if (ymid > 1.) ymid = 1. / ymid;
+                    P.refined[e] = make_double2(P.fs / xmid, ymid);
+                }
+                have = false;
+            }
+        }
+    }
     }
 }
 
@@ -812,6 +1066,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
 
     const char* rv = getenv("VBX_PITCH_REFINE");
     const bool refine_v0 = rv && rv[0] == 'v' && rv[1] == '0';  // the first (warp per candidate) version, kept for A/B runs
+    const bool refine_v1 = rv && rv[0] == 'v' && rv[1] == '1';  // lockstep groups of four (no queue), kept for A/B runs
     for (int64_t f0 = 0; f0 < fr->n_frames; f0 += slab) {
         P.frame0 = f0;
         P.n_frames = (fr->n_frames - f0 < slab) ? fr->n_frames - f0 : slab;
@@ -822,8 +1077,10 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         VBX_CHECK_LAUNCH(ctx, "pitch_lag_kernel");
         if (refine_v0) {
             pitch_refine_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P);
-        } else {
+        } else if (refine_v1) {
             pitch_refine8_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
+        } else {
+            pitch_refine8q_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
         }
         VBX_CHECK_LAUNCH(ctx, "pitch_refine_kernel");
         pitch_finalize_kernel<<<(unsigned)((P.n_frames + 3) / 4), 128, 0, ctx->stream>>>(P, cand_out, max_cand, n_cand_out,
