@@ -47,7 +47,7 @@ struct PitchParams {
     PitchCand* list;        // [S·cap] work list
     double2* refined;       // [S·cap] (frequency, strength) per work-list entry
     int2* range;            // [S] (first list entry, count) per frame
-    unsigned long long* counter;  // number of list entries
+    unsigned long long* counter;  // [0] number of list entries, [1] tile cursor of the refine kernel
     int64_t frame0;         // first frame of this slab inside the batch
     int64_t n_frames;       // frames in this slab
     int64_t stride, seg_frames, seg_stride;
@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
     __shared__ float s_key[kRefineTile];
     __shared__ unsigned short s_ord[kRefineTile];
     __shared__ int s_next;
+    __shared__ long long s_tile;
     const int offset = -P.ixmax - 1;
     const int nx = P.ixmax - offset;
     const int ylen = 2 * N;
@@ -635,10 +636,18 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
     const double sgn = (l8 & 1) ? -1.0 : 1.0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    for (long long tile0 = (long long)blockIdx.x * kRefineTile; tile0 < total; tile0 += (long long)gridDim.x * kRefineTile) {
-    const int tcnt = (int)min((long long)kRefineTile, total - tile0);
+    // tiles are handed out dynamically (P.counter[1]): the grid is exactly the resident CTAs and none of them idles
+    // while another still has a backlog
+    while (true) {
     __syncthreads();  // the previous tile's order is no longer read
-    if (threadIdx.x == 0) s_next = 0;
+    if (threadIdx.x == 0) {
+        s_tile = (long long)atomicAdd(P.counter + 1, 1ULL);
+        s_next = 0;
+    }
+    __syncthreads();
+    const long long tile0 = s_tile * kRefineTile;
+    if (tile0 >= total) break;
+    const int tcnt = (int)min((long long)kRefineTile, total - tile0);
     for (int i = threadIdx.x; i < tcnt; i += blockDim.x) s_key[i] = (float)P.list[tile0 + i].n;
     __syncthreads();
     for (int i = threadIdx.x; i < tcnt; i += blockDim.x) {
@@ -1070,7 +1079,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     for (int64_t f0 = 0; f0 < fr->n_frames; f0 += slab) {
         P.frame0 = f0;
         P.n_frames = (fr->n_frames - f0 < slab) ? fr->n_frames - f0 : slab;
-        VBX_CUDA(ctx, cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), ctx->stream));
+        VBX_CUDA(ctx, cudaMemsetAsync(P.counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
         const int64_t grid = (P.n_frames + fpc - 1) / fpc;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
         pitch_lag_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
@@ -1080,7 +1089,14 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         } else if (refine_v1) {
             pitch_refine8_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
         } else {
-            pitch_refine8q_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
+            static int resident = 0;  // CTAs of the queue-fed kernel that fit one SM
+            if (!resident) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pitch_refine8q_kernel, 128, 0) != cudaSuccess || resident < 1) {
+                    cudaGetLastError();
+                    resident = 4;
+                }
+            }
+            pitch_refine8q_kernel<<<ctx->sm_count * resident, 128, 0, ctx->stream>>>(P);
         }
         VBX_CHECK_LAUNCH(ctx, "pitch_refine_kernel");
         pitch_finalize_kernel<<<(unsigned)((P.n_frames + 3) / 4), 128, 0, ctx->stream>>>(P, cand_out, max_cand, n_cand_out,
