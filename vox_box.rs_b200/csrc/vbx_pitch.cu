@@ -203,43 +203,41 @@ __global__ void __launch_bounds__(512) pitch_lag_kernel(const PitchParams P) {
         // periodic.rs:417-439: maxima of y[0..ixmax), parabolic frequency, (min, max) filter
         const int ixmax = P.ixmax;
         const double offset = -(double)ixmax - 1.0;
-        int count = 0, start = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            int k = 0;
-            for (int base = 1; base + 1 < ixmax; base += 32) {
-                const int cidx = base + lane;
-                bool keep = false;
-                double nn = 0.0;
-                if (cidx + 1 < ixmax) {
-                    const double peak = yrow[cidx], rev = yrow[cidx - 1], fwd = yrow[cidx + 1];
-                    if (rev < peak && fwd < peak) {
-                        const double dr = 0.5 * (fwd - rev);
-                        const double d2r = 2. * peak - (rev - fwd);  // sign quirk, periodic.rs:424
-                        const double freq = P.fs / ((double)cidx + dr / d2r);
-                        keep = (freq == 0.) || (freq > P.fmin && freq < P.fmax);
-                        nn = P.fs / freq - offset;
-                    }
+        // one pass: the start abscissae are parked in the frame's (now dead) sample buffer, the frame's slice of the
+        // work list is reserved once the count is known, then the entries are written out
+        double* stage = reinterpret_cast<double*>(xs_all + (size_t)qf * P.xs_words);  // xs_words·4 bytes >= (ixmax/2 + 1)·8
+        int k = 0;
+        for (int base = 1; base + 1 < ixmax; base += 32) {
+            const int cidx = base + lane;
+            bool keep = false;
+            double nn = 0.0;
+            if (cidx + 1 < ixmax) {
+                const double peak = yrow[cidx], rev = yrow[cidx - 1], fwd = yrow[cidx + 1];
+                if (rev < peak && fwd < peak) {
+                    const double dr = 0.5 * (fwd - rev);
+                    const double d2r = 2. * peak - (rev - fwd);  // sign quirk, periodic.rs:424
+                    const double freq = P.fs / ((double)cidx + dr / d2r);
+                    keep = (freq == 0.) || (freq > P.fmin && freq < P.fmax);
+                    nn = P.fs / freq - offset;
                 }
-                const unsigned bal = __ballot_sync(FULL, keep);
-                if (pass == 1 && keep) {
-                    const int kk = k + __popc(bal & ((1u << lane) - 1u));
-                    PitchCand e;
-                    e.frame = (int)(f_first + qf);
-                    e.k = kk;
-                    e.n = nn;
-                    P.list[(size_t)start + kk] = e;
-                }
-                k += __popc(bal);
             }
-            if (pass == 0) {
-                count = k;
-                unsigned long long pos = 0;
-                if (lane == 0) {
-                    pos = atomicAdd(P.counter, (unsigned long long)count);
-                    P.range[f_first + qf] = make_int2((int)pos, count);
-                }
-                start = (int)__shfl_sync(FULL, pos, 0);
-            }
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (keep) stage[k + __popc(bal & ((1u << lane) - 1u))] = nn;
+            k += __popc(bal);
+        }
+        const int count = k;
+        unsigned long long pos = 0;
+        if (lane == 0) {
+            pos = atomicAdd(P.counter, (unsigned long long)count);
+            P.range[f_first + qf] = make_int2((int)pos, count);
+        }
+        const int start = (int)__shfl_sync(FULL, pos, 0);  // also orders the staging writes before the reads below
+        for (int i = lane; i < count; i += 32) {
+            PitchCand e;
+            e.frame = (int)(f_first + qf);
+            e.k = i;
+            e.n = stage[i];
+            P.list[(size_t)start + i] = e;
         }
     }
 }
