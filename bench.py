@@ -497,6 +497,13 @@ def run_ours(args, cfg, rank, world, local_rank):
 
         # ---- end to end through the host-pointer C-ABI call ------------------------------------------
         e2e_steps = max(3, min(args.steps, 20 if wl.h2d < (1 << 30) else 5))
+        if args.device_only:
+            if rank == 0:
+                _, _, kernels = wl.roofline(prof, args.steps, peaks, 1.0, "")
+                print(json.dumps({"device_only": True, "value": F * world * args.steps / (ms * 1e-3), "unit": "frames/s",
+                                  "ms_per_step": ms / args.steps, "gpu_launches": launches,
+                                  "kernel_share": {k: v["share"] for k, v in kernels.items()}}))
+            return
         for _ in range(3):
             wl.e2e_step()
         barrier()
@@ -560,6 +567,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--utts", type=int, default=None, help="utterances per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--device-only", action="store_true",
+                    help="device-resident steps only (no e2e / cpu legs): the command the ncu launch lists under profiles/ are taken with")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

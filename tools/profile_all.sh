@@ -3,8 +3,7 @@
 set -x
 mkdir -p gpurun_out
 for c in c2 c3 c4 c5; do
-  extra=""; [ $c = c3 ] && extra="--utts 1125"
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_${c}.csv python bench.py --config $c --steps 2 --warmup 1 --no-cpu $extra > gpurun_out/ncu_bench_${c}.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${c}.csv python bench.py --config $c --steps 2 --warmup 3 --device-only > gpurun_out/ncu_bench_${c}.log 2>&1
 done
 full() { # name regex command...
   local name=$1 rx=$2; shift 2
