@@ -166,6 +166,25 @@ def make_corpus(cfg, rank):
 # ------------------------------------------------------------------------------------------------
 # CPU port (oracle) of each config: used by --impl reference and by the cpu_baseline leg
 # ------------------------------------------------------------------------------------------------
+def numa_bind(gpu_index):
+    """Bind the calling thread to the CPUs NVML reports as local to the GPU; returns the previous mask (or None)."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= before
+        if cpus and cpus != before:
+            os.sched_setaffinity(0, cpus)
+            return before
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     """Host threads for the CPU arm: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
     would silently make the "all host threads" baseline single-threaded, so the count is passed explicitly)."""
@@ -471,6 +490,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # Run this rank on the CPUs next to its GPU while the pinned host buffers are allocated and the end-to-end leg runs
+    # (NUMA-local staging memory: with 8 ranks on a two-socket host the H2D copies otherwise cross the socket link).
+    # The original mask is restored before the CPU-baseline leg, which uses every host core.
+    cpus_before = numa_bind(local_rank)
     ctx = vb.Context(local_rank)  # raises without the CUDA library / a device: no CPU fallback
     audio = make_corpus(cfg, rank)
     wl = Workload(ctx, vb, cfg, audio)
@@ -550,6 +573,8 @@ def run_ours(args, cfg, rank, world, local_rank):
             "clocks": clocks.summary(),
             "checksum": checksum,
         }
+        if cpus_before:
+            os.sched_setaffinity(0, cpus_before)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(cfg, audio)
         print(json.dumps(line), flush=True)
