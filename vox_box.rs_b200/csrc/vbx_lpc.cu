@@ -562,12 +562,18 @@ bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames,
 template <typename TIn>
 int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_out, void* kc_out, int out_dtype,
                bool do_levinson) {
-    static lpc_kernel_t table[kMaxFastLags + 1] = {nullptr};
-    static bool filled = false;
-    if (!filled) {
-        LpcTable<TIn, kMaxFastLags>::fill(table);
-        filled = true;
-    }
+    // kernel tables: filled once, thread-safely (C++11 static initialisation)
+    struct Tables {
+        lpc_kernel_t general[kMaxFastLags + 1] = {nullptr};
+        lpc_kernel_t chunk16[kChunk + 1] = {nullptr};
+        Tables() {
+            LpcTable<TIn, kMaxFastLags>::fill(general);
+            Lpc16Table<TIn, kChunk>::fill(chunk16);
+        }
+    };
+    static const Tables tables;
+    const lpc_kernel_t* table = tables.general;
+    const lpc_kernel_t* table16 = tables.chunk16;
     const double* win = nullptr;
     int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win, fr->dtype);
     if (st != VBX_OK) return st;
@@ -575,8 +581,6 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     LpcParams P;
     memset(&P, 0, sizeof(P));
     size_t smem = 0;
-    static lpc_kernel_t table16[kChunk + 1] = {nullptr};
-    if (!table16[2]) Lpc16Table<TIn, kChunk>::fill(table16);
     const bool fused16 = plan_fused16(ctx, fr->frame_len, fr->frame_stride, vbx_frames_per_segment(fr), L, &P, &smem);
     const bool fused_ok =
         fused16 || ((L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem));
@@ -725,12 +729,12 @@ int vbx_lpc_host(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* r_out,
 int vbx_lpc_levinson(vbx_ctx* ctx, const void* r, int32_t r_dtype, int64_t n_frames, int32_t r_stride, int32_t p,
                      void* ac_out, void* kc_out, int32_t out_dtype) {
     if (!ctx) return VBX_ERR_BADARG;
-    static lev_kernel_t table[kMaxLevinsonOrder + 1] = {nullptr};
-    static bool filled = false;
-    if (!filled) {
-        LevTable<kMaxLevinsonOrder>::fill(table);
-        filled = true;
-    }
+    struct Tables {
+        lev_kernel_t t[kMaxLevinsonOrder + 1] = {nullptr};
+        Tables() { LevTable<kMaxLevinsonOrder>::fill(t); }
+    };
+    static const Tables tables;  // filled once, thread-safely
+    const lev_kernel_t* table = tables.t;
     VBX_REQUIRE(ctx, p >= 1 && p <= kMaxLevinsonOrder, "LPC order must be in 1..%d", kMaxLevinsonOrder);
     VBX_REQUIRE(ctx, r_stride >= p + 1, "r_stride must be >= p + 1 (lpc_mut reads self[0..=p])");
     VBX_REQUIRE(ctx, r_dtype == VBX_F32 || r_dtype == VBX_F64, "r_dtype must be VBX_F32 or VBX_F64");

@@ -19,7 +19,8 @@ struct vbx_host_out {
 // launch(chunk_frames_view_on_device, first_frame, first_segment, outs_with_dev_set) -> status
 template <class Launch>
 static int vbx_run_chunked(vbx_ctx* ctx, const vbx_frames* fr, vbx_host_out* outs, int n_outs, Launch launch,
-                           int max_chunks = 0 /* 0 = no limit; paths with a latency-bound per-chunk kernel ask for few, large chunks */) {
+                           int max_chunks = 0 /* 0 = no limit; paths with a latency-bound per-chunk kernel ask for few, large chunks */,
+                           size_t target_bytes = (size_t)24 << 20 /* input bytes per chunk; compute-bound paths ask for more */) {
     const int64_t F = fr->n_frames;
     const size_t es = vbx_dtype_size(fr->dtype);
     const bool segmented = fr->frames_per_segment > 0;
@@ -30,8 +31,8 @@ static int vbx_run_chunked(vbx_ctx* ctx, const vbx_frames* fr, vbx_host_out* out
     const int64_t unit_extent = segmented ? (J - 1) * fr->frame_stride + fr->frame_len : fr->frame_len;
     size_t out_per_frame = 0;
     for (int i = 0; i < n_outs; ++i) out_per_frame += outs[i].host ? outs[i].bytes_per_frame : 0;
-    // chunk size: ~24 MB of input per chunk, at least 4 chunks when there is enough work to overlap
-    size_t target = (size_t)24 << 20;
+    // chunk size: `target_bytes` of input per chunk (24 MB unless the caller says otherwise; VBX_HOST_CHUNK_MB overrides)
+    size_t target = target_bytes;
     if (const char* e = getenv("VBX_HOST_CHUNK_MB")) target = (size_t)atoll(e) << 20;
     int64_t units_per_chunk = (int64_t)(target / ((size_t)unit_stride * es + 1)) + 1;
     if (max_chunks > 0 && !getenv("VBX_HOST_CHUNK_MB")) {

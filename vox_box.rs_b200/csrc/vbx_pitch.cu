@@ -1087,13 +1087,14 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         } else if (refine_v1) {
             pitch_refine8_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
         } else {
-            static int resident = 0;  // CTAs of the queue-fed kernel that fit one SM
-            if (!resident) {
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pitch_refine8q_kernel, 128, 0) != cudaSuccess || resident < 1) {
+            static const int resident = [] {  // CTAs of the queue-fed kernel that fit one SM (computed once, thread-safely)
+                int r = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pitch_refine8q_kernel, 128, 0) != cudaSuccess || r < 1) {
                     cudaGetLastError();
-                    resident = 4;
+                    r = 4;
                 }
-            }
+                return r;
+            }();
             pitch_refine8q_kernel<<<ctx->sm_count * resident, 128, 0, ctx->stream>>>(P);
         }
         VBX_CHECK_LAUNCH(ctx, "pitch_refine_kernel");
@@ -1146,7 +1147,7 @@ int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, d
     return vbx_run_chunked(ctx, frames, outs, 3, [&](const vbx_frames* dfr, int64_t, int64_t, vbx_host_out* o) -> int {
         return vbx_pitch(ctx, dfr, sample_rate, threshold, min_hz, max_hz, max_candidates, o[0].dev, (int32_t*)o[1].dev,
                          (uint8_t*)o[2].dev, out_dtype);
-    });
+    }, 0, (size_t)96 << 20);  // compute-bound: the copies hide behind the kernels anyway, larger chunks mean fewer kernel tails
 }
 
 int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_frames, int32_t max_candidates, void* out) {
