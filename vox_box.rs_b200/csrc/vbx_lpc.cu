@@ -44,6 +44,7 @@ struct LpcParams {
     int span_words;        // shared-memory words reserved for the padded span
     int out_f64;           // outputs are double (else float)
     int do_levinson;
+    int straddle;          // lpc_fused16_kernel: CTAs take G consecutive frames of the batch, across segment boundaries
 };
 
 // Levinson–Durbin exactly as spectrum.rs:63-84 (no zero guard: err == 0 propagates inf/NaN).
@@ -522,7 +523,8 @@ bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames,
         const int G = threads / halves;
         const int64_t span = (int64_t)(G - 1) * sv + n;
         if (span * (int64_t)sv >= (1LL << 32)) continue;
-        const int64_t span_words = span + pad * (span / sv + 1) + 4;
+        // room for a span staged as two pieces (a CTA that crosses into the next utterance, P.straddle)
+        const int64_t span_words = (int64_t)G * (sv + pad) + 2 * ((int64_t)n + pad * (n / sv + 1)) + 8;
         const size_t stage_bytes = (size_t)G * (3 * L - 1) * sizeof(double);
         size_t span_bytes = ((size_t)span_words * sizeof(float) + 15) & ~(size_t)15;
         const size_t bytes = (size_t)n * sizeof(double) + (span_bytes > stage_bytes ? span_bytes : stage_bytes);
@@ -600,7 +602,12 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
         P.do_levinson = do_levinson ? 1 : 0;
         lpc_kernel_t kern = fused16 ? table16[L] : table[L];
         VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t grid = (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
+        // 16-aligned kernel, several utterances of at least one CTA's worth of overlapped frames: CTAs take G consecutive
+        // frames of the batch (an utterance of 998 frames otherwise leaves 26 of its last CTA's 64 frame slots empty)
+        P.straddle = (fused16 && fr->n_frames > P.seg_frames && P.seg_frames >= P.frames_per_cta && P.stride <= (int64_t)P.n &&
+                      !getenv("VBX_LPC16_NO_STRADDLE")) ? 1 : 0;
+        const int64_t grid = P.straddle ? (fr->n_frames + P.frames_per_cta - 1) / P.frames_per_cta
+                                        : (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
         kern<<<(unsigned)grid, P.threads, smem, ctx->stream>>>(P);
         VBX_CHECK_LAUNCH(ctx, fused16 ? "lpc_fused16_kernel" : "lpc_fused_kernel");

@@ -102,15 +102,34 @@ __global__ void __maxnreg__(96) lpc_fused16_kernel(const LpcParams P) {
 
     const int tid = threadIdx.x;
     const int G = P.frames_per_cta;
-    const int64_t seg = blockIdx.x / P.ctas_per_seg;
-    const int64_t j0 = (int64_t)(blockIdx.x - seg * P.ctas_per_seg) * G;
-    const int64_t g0 = seg * P.seg_frames + j0;
-    const int Gc = (int)min((int64_t)G, P.seg_frames - j0);
     const int n = P.n, sv = P.sv, pad = P.pad;
+    // Frames of the batch are numbered through the segments (utterances).  With P.straddle a CTA takes G consecutive
+    // frames of the BATCH — when they cross into the next segment its span is staged as two pieces (nA frames of this
+    // segment, nB of the next) — so only the batch's last CTA is partial; otherwise every segment gets its own CTAs.
+    int64_t seg, j0, g0;
+    int Gc, nA;
+    if (P.straddle) {
+        g0 = (int64_t)blockIdx.x * G;
+        Gc = (int)min((int64_t)G, P.n_frames - g0);
+        seg = g0 / P.seg_frames;
+        j0 = g0 - seg * P.seg_frames;
+        nA = (int)min((int64_t)Gc, P.seg_frames - j0);
+    } else {
+        seg = blockIdx.x / P.ctas_per_seg;
+        j0 = (int64_t)(blockIdx.x - seg * P.ctas_per_seg) * G;
+        g0 = seg * P.seg_frames + j0;
+        Gc = (int)min((int64_t)G, P.seg_frames - j0);
+        nA = Gc;
+    }
+    const int nB = Gc - nA;
+    // second piece: right after the first piece's padded span, 16-byte aligned
+    const int totalA = (nA - 1) * sv + n;
+    const int offB = (totalA + pad * ((totalA - 1) / sv) + 3) & ~3;
     const TIn* __restrict__ base = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride;
 
     for (int i = tid; i < n; i += P.threads) s_win[i] = __ldg(P.win + i);
-    stage_span16<TIn>(P, base, j0, Gc, s_span);
+    stage_span16<TIn>(P, base, j0, nA, s_span);
+    if (nB > 0) stage_span16<TIn>(P, base + P.seg_stride, 0, nB, s_span + offB);
     __syncthreads();
 
     // warp → (32 frames, half): with two halves per frame (P.k == 2) even warps walk the first chunks of their 32
@@ -131,7 +150,7 @@ __global__ void __maxnreg__(96) lpc_fused16_kernel(const LpcParams P) {
         const int c = q ? C - nch : 0;
         const int blk = c / cpb;
         int left = cpb - (c - blk * cpb);
-        const float* sp = s_span + g * (sv + pad) + c * kChunk + pad * blk;
+        const float* sp = s_span + (g < nA ? g * (sv + pad) : offB + (g - nA) * (sv + pad)) + c * kChunk + pad * blk;
         const double* wp = s_win + c * kChunk;
         int it = 0;
         for (; it < pre; ++it) {
