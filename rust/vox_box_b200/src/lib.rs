@@ -118,6 +118,26 @@ pub mod ffi {
                               out_dtype: i32) -> c_int;
         pub fn vbx_pitch_extract(ctx: *mut vbx_ctx, cand: *const c_void, dtype: i32, n_frames: i64, max_candidates: i32,
                                  out: *mut c_void) -> c_int;
+        pub fn vbx_pitch_viterbi(ctx: *mut vbx_ctx, cand: *const c_void, dtype: i32, n_cand: *const i32, n_segments: i64,
+                                 frames_per_segment: i64, max_candidates: i32, voiced_unvoiced_cost: f64, octave_jump_cost: f64,
+                                 octave_cost: f64, ceiling_hz: f64, path_out: *mut c_void, index_out: *mut i32) -> c_int;
+        pub fn vbx_autocorrelate_ring(ctx: *mut vbx_ctx, rings: *const c_void, dtype: i32, n_rings: i64, capacity: i64,
+                                      heads: *const i64, n: i32, n_lags: i32, r_out: *mut c_void, out_dtype: i32) -> c_int;
+        pub fn vbx_lpc_to_resonances(ctx: *mut vbx_ctx, lpc: *const c_void, lpc_dtype: i32, n_frames: i64, lpc_stride: i32, p: i32,
+                                     lpc_has_leading_one: i32, sample_rate: f64, strict_im: i32, status_in: *const u8,
+                                     res_out: *mut c_void, res_slots: i32, nres_out: *mut i32, roots_out: *mut c_void,
+                                     status_out: *mut u8, out_dtype: i32, precision: i32) -> c_int;
+        pub fn vbx_window_table_host(window: c_int, n: i32, out: *mut f64) -> c_int;
+        pub fn vbx_malloc_host(ctx: *mut vbx_ctx, bytes: usize, host_out: *mut *mut c_void) -> c_int;
+        pub fn vbx_free_host(ctx: *mut vbx_ctx, host: *mut c_void) -> c_int;
+        pub fn vbx_memset(ctx: *mut vbx_ctx, dev: *mut c_void, value: c_int, bytes: usize) -> c_int;
+        pub fn vbx_ctx_stream(ctx: *mut vbx_ctx) -> *mut c_void;
+        pub fn vbx_version() -> c_int;
+        pub fn vbx_device_sm_count(ctx: *mut vbx_ctx) -> c_int;
+        pub fn vbx_kernel_launches(ctx: *mut vbx_ctx) -> i64;
+        pub fn vbx_timer_start(ctx: *mut vbx_ctx) -> c_int;
+        pub fn vbx_timer_stop_ms(ctx: *mut vbx_ctx, ms_out: *mut f32) -> c_int;
+        pub fn vbx_measure_peaks(ctx: *mut vbx_ctx, fp32_tflops: *mut f64, fp64_tflops: *mut f64) -> c_int;
         pub fn vbx_interpolate_sinc(ctx: *mut vbx_ctx, y: *const f64, n_series: i64, y_len: i64, offset: i64, nx: i64,
                                     x: *const f64, n_points: i64, max_depth: i64, out: *mut f64) -> c_int;
         pub fn vbx_improve_extremum(ctx: *mut vbx_ctx, y: *const f64, n_series: i64, y_len: i64, offset: i64, nx: i64,
@@ -231,6 +251,25 @@ impl Context {
         Ok(out)
     }
 
+    // ---- periodic.rs:291-304 `impl Autocorrelate for VecDeque<T>`: the same fold on a ring buffer --------------
+    // The deque's storage is uploaded as it lies in memory (two slices = one ring with a head) and unrolled on the device.
+    pub fn autocorrelate_deque(&self, x: &std::collections::VecDeque<f32>, n_coeffs: usize) -> VoxBoxResult<Vec<f64>> {
+        let (front, back) = x.as_slices();
+        // ring = back ++ front, logical element i = ring[(head + i) mod capacity] with head = back.len()
+        let mut ring: Vec<f32> = Vec::with_capacity(x.len());
+        ring.extend_from_slice(back);
+        ring.extend_from_slice(front);
+        let heads = [back.len() as i64];
+        let dev = DeviceBuf::from_host(self, &ring)?;
+        let dheads = DeviceBuf::from_host(self, &heads)?;
+        let out = DeviceBuf::<f64>::new(self, n_coeffs)?;
+        self.check(unsafe {
+            ffi::vbx_autocorrelate_ring(self.raw, dev.ptr, ffi::VBX_F32, 1, ring.len() as i64, dheads.ptr as *const i64,
+                                        ring.len() as i32, n_coeffs as i32, out.ptr, ffi::VBX_F64)
+        })?;
+        out.to_host(self)
+    }
+
     // ---- spectrum.rs:50-92 LPC::{lpc_mut, lpc} on an already autocorrelated buffer ------------------
     pub fn lpc(&self, r: &[f64], n_coeffs: usize) -> VoxBoxResult<Vec<f64>> {
         let dev = DeviceBuf::from_host(self, r)?;
@@ -294,6 +333,32 @@ impl Context {
         self.check(st[0] as c_int)?;
         cand.truncate(n[0] as usize);
         Ok(cand)
+    }
+
+    // ---- periodic.rs:320-354 PitchExtractor: the strongest candidate of every frame (`candidates[frame][0]`) --------------
+    // `candidates` = one `pitch()` result per frame.  With `viterbi = true` the opt-in path finder runs instead (the
+    // reference declares `voiced_unvoiced_cost` but never uses it: periodic.rs:394-395); `false` is the reference's behaviour.
+    pub fn pitch_extract(&self, candidates: &[Vec<Pitch<f64>>], voiced_unvoiced_cost: f64, viterbi: bool) -> VoxBoxResult<Vec<Pitch<f64>>> {
+        let frames = candidates.len();
+        let cap = candidates.iter().map(|c| c.len()).max().unwrap_or(0).max(1);
+        let mut flat = vec![Pitch { frequency: 0f64, strength: 0f64 }; frames * cap];
+        let mut counts = vec![0i32; frames];
+        for (f, c) in candidates.iter().enumerate() {
+            flat[f * cap..f * cap + c.len()].copy_from_slice(c);
+            counts[f] = c.len() as i32;
+        }
+        let dev = DeviceBuf::from_host(self, &flat)?;
+        let out = DeviceBuf::<Pitch<f64>>::new(self, frames)?;
+        if viterbi {
+            let dn = DeviceBuf::from_host(self, &counts)?;
+            self.check(unsafe {
+                ffi::vbx_pitch_viterbi(self.raw, dev.ptr, ffi::VBX_F64, dn.ptr as *const i32, 1, frames as i64, cap as i32,
+                                       voiced_unvoiced_cost, 0.35, 0.01, 600.0, out.ptr, ptr::null_mut())
+            })?;
+        } else {
+            self.check(unsafe { ffi::vbx_pitch_extract(self.raw, dev.ptr, ffi::VBX_F64, frames as i64, cap as i32, out.ptr) })?;
+        }
+        out.to_host(self)
     }
 
     // ---- spectrum.rs:371-441 MFCC::mfcc (frame already windowed by the caller) ----------------------------------------
