@@ -48,6 +48,16 @@ def test_python_binding_declares_every_function():
     assert not undeclared, f"ctypes signatures missing for: {undeclared}"
 
 
+def test_rust_shim_declares_every_function():
+    """rust/vox_box_b200 (source only: no Rust toolchain here) binds every entry point the header declares."""
+    fns, _ = _declared_symbols()
+    rs = open(os.path.join(ROOT, "rust", "vox_box_b200", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (vbx_\w+)\s*\(", rs))
+    missing = [f for f in fns if f not in bound]
+    assert not missing, f"missing from the Rust extern block: {missing}"
+    assert not [f for f in bound if f not in fns], "Rust extern block names a function the header does not declare"
+
+
 def test_formant_estimate_constants():  # lib.rs:27-28
     lib = vb.load_library()
     male = (C.c_double * 4).in_dll(lib, "VBX_MALE_FORMANT_ESTIMATES")
