@@ -257,6 +257,197 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// lpc_roots_pair_kernel: the fp32 fast path for the fused LPC → resonances call when the caller does not ask for the
+// roots themselves.  The LPC polynomial is REAL, so every complex root comes with its conjugate: after a Laguerre solve
+// (same start point −2−2i, same update formula and n as polynomial.rs:34-72) the pair is divided out as the real
+// quadratic x² − 2·Re(z)·x + |z|² (a real root as x − z), the working polynomial stays real and its degree drops by
+// two per solve: 5 solves over degrees 12, 10, 8, 6, 4 instead of the reference's 10 over 12 … 3 — 40 instead of 75
+// Horner coefficient steps per iteration round and half the Laguerre updates.  The set of roots is the same (they are
+// the roots of the same polynomial; each candidate is then polished in fp64 on the ORIGINAL coefficients exactly as in
+// lpc_roots_rt_kernel), only the order in which they are found differs — which is why a call that wants `roots_out`
+// (find_roots order) takes lpc_roots_rt_kernel instead.  Resonance counts and values are checked against the oracle in
+// tests/test_gpu_formants.py, tests/test_gpu_full_size.py and tools/parity_scale.py.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const RootsParams Q, const int P) {
+    extern __shared__ __align__(16) unsigned char roots_smem[];
+    constexpr int T = kRootsThreads;
+    typedef float TR;
+    const unsigned FULL = 0xffffffffu;
+    double* a_s = reinterpret_cast<double*>(roots_smem);                    // [P+1][T] original real coefficients
+    double* st_s = a_s + (size_t)(P + 1) * T;                               // [P+2][T] staged frequencies (rows 0..P/2) | bandwidths
+    vcx<TR>* r_s = reinterpret_cast<vcx<TR>*>(st_s + (size_t)(P + 2) * T);  // [P][T]   roots (im >= 0 first of a pair)
+    float* c_s = reinterpret_cast<float*>(r_s + (size_t)P * T);             // [P+1][T] working polynomial (real)
+    const int tid = threadIdx.x;
+    const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
+    const bool in_range = f_raw < Q.n_frames;
+    const int64_t f = in_range ? f_raw : Q.n_frames - 1;
+    const int R = Q.R;
+    auto write_res = [&](int slot, double fr_, double bw_) {
+        if (Q.out_f64) {
+            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            o[0] = fr_; o[1] = bw_;
+        } else {
+            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            o[0] = (float)fr_; o[1] = (float)bw_;
+        }
+    };
+    const bool lpc_failed = Q.status_in && Q.status_in[f] != VBX_OK;
+    auto lpc_at = [&](int idx) -> double {
+        return Q.lpc_f64 ? reinterpret_cast<const double*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx]
+                         : (double)reinterpret_cast<const float*>(Q.lpc)[(size_t)f * Q.lpc_stride + idx];
+    };
+    for (int k = 0; k <= P; ++k) {
+        const double v = (k < P) ? lpc_at((P - k) - (Q.lpc_has_one ? 0 : 1)) : (Q.lpc_has_one ? lpc_at(0) : 1.0);
+        a_s[k * T + tid] = v;
+        c_s[k * T + tid] = (float)v;
+    }
+    const TR nn = (TR)((P - 1) * P), nref = (TR)P;
+    int M = P, it = 0, nroots = 0;
+    vcx<TR> z = cmk<TR>((TR)-2, (TR)-2);
+    bool active = (P >= 3) && !lpc_failed;
+#pragma unroll 1
+    while (true) {
+        const int Mmax = __reduce_max_sync(FULL, active ? M : 0);
+        if (Mmax < 3) break;
+        // Horner triple (P, P', P''/2) at z from the warp's largest degree: coefficients above a lane's own degree are 0
+        vcx<TR> a0 = cmk<TR>(c_s[Mmax * T + tid], (TR)0), a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
+#pragma unroll 4
+        for (int j = Mmax - 1; j >= 0; --j) {
+            const TR cj = c_s[j * T + tid];
+            a2 = cfma(a2, z, a1);
+            a1 = cfma(a1, z, a0);
+            a0 = cfma(a0, z, cmk<TR>(cj, (TR)0));
+        }
+        if (active) {
+            bool done = false;
+            if (cnorm_sqr(a0) <= (TR)1.0e-32) {
+                done = true;
+            } else {
+                const vcx<TR> step = laguerre_step<TR, true>(a0, a1, a2, nn, nref);
+                z = cadd(z, step);
+                const TR eps = (TR)3.0e-7;
+                if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) done = true;
+                if (++it == 20) done = true;
+            }
+            if (done) {
+                // a root this close to the real axis (|arg| < 1e-5: below 0.1 Hz at any audio rate) is divided out as real
+                const bool real_root = fabsf(z.im) <= (TR)1.0e-5 * fabsf(z.re);
+                if (real_root) {
+                    r_s[nroots * T + tid] = cmk<TR>(z.re, (TR)0);
+                    ++nroots;
+                    // synthetic division by (x − r): b[i−1] = c[i] + r·b[i]
+                    TR carry = c_s[M * T + tid];
+                    c_s[M * T + tid] = (TR)0;
+#pragma unroll 4
+                    for (int i = M - 1; i >= 0; --i) {
+                        const TR old = c_s[i * T + tid];
+                        c_s[i * T + tid] = carry;
+                        carry = fmaf(carry, z.re, old);
+                    }
+                    M -= 1;
+                } else {
+                    r_s[nroots * T + tid] = cmk<TR>(z.re, fabsf(z.im));
+                    r_s[(nroots + 1) * T + tid] = cmk<TR>(z.re, -fabsf(z.im));
+                    nroots += 2;
+                    // synthetic division by x² + p·x + q, p = −2·Re z, q = |z|²: b[i−2] = c[i] − p·b[i−1] − q·b[i]
+                    const TR pq = (TR)-2 * z.re, qq = cnorm_sqr(z);
+                    TR b1 = (TR)0, b2 = (TR)0;  // b[i−1+1], b[i+1] of the previous step
+#pragma unroll 4
+                    for (int i = M; i >= 2; --i) {
+                        const TR b0 = fmaf(-pq, b1, fmaf(-qq, b2, c_s[i * T + tid]));
+                        c_s[i * T + tid] = b2;   // quotient coefficient of x^i (slots M, M−1 become 0, the rest shift down by 2)
+                        b2 = b1;
+                        b1 = b0;
+                    }
+                    // after the loop: b1 = b[0], b2 = b[1]; quotient x^1 and x^0 coefficients
+                    c_s[1 * T + tid] = b2;
+                    c_s[0 * T + tid] = b1;
+                    M -= 2;
+                }
+                it = 0;
+                z = cmk<TR>((TR)-2, (TR)-2);
+                active = (M >= 3);
+            }
+        }
+    }
+    if (lpc_failed) {
+        if (in_range) {
+            if (Q.status_out) Q.status_out[f] = Q.status_in[f];
+            if (Q.nres_out) Q.nres_out[f] = 0;
+            if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
+        }
+        return;
+    }
+    if (!in_range) return;
+    // tail: what is left has degree 2, 1 or 0 (real coefficients)
+    if (M == 2) {
+        const TR q0 = c_s[tid], q1 = c_s[T + tid], q2 = c_s[2 * T + tid];
+        const TR disc = q1 * q1 - (TR)4 * q2 * q0;
+        const TR inv = (TR)1 / ((TR)2 * q2);
+        if (disc < (TR)0) {
+            const TR sq = sqrtf(-disc);
+            r_s[nroots * T + tid] = cmk<TR>(-q1 * inv, fabsf(sq * inv));
+            r_s[(nroots + 1) * T + tid] = cmk<TR>(-q1 * inv, -fabsf(sq * inv));
+        } else {
+            const TR sq = sqrtf(disc);
+            r_s[nroots * T + tid] = cmk<TR>((-q1 + sq) * inv, (TR)0);
+            r_s[(nroots + 1) * T + tid] = cmk<TR>((-q1 - sq) * inv, (TR)0);
+        }
+        nroots += 2;
+    } else if (M == 1) {
+        r_s[nroots * T + tid] = cmk<TR>(-c_s[tid] / c_s[T + tid], (TR)0);
+        nroots += 1;
+    }
+    // resonances: fp64 polish (Newton on the ORIGINAL polynomial) of the roots that can become resonances, from_root
+    int cnt = 0;
+#pragma unroll 1
+    for (int k = 0; k < nroots; ++k) {
+        const vcx<TR> zr = r_s[k * T + tid];
+        vcx<double> zz = cmk<double>((double)zr.re, (double)zr.im);
+        const bool cand = Q.strict_im ? (zz.im > 0.0) : (zz.im >= 0.0);
+        if (cand && Q.polish_steps > 0) {
+            for (int s = 0; s < Q.polish_steps; ++s) {
+                vcx<double> p0 = cmk<double>(a_s[P * T + tid], 0.0), p1 = cmk<double>(0.0, 0.0);
+#pragma unroll 4
+                for (int j = P - 1; j >= 0; --j) {
+                    p1 = cfma(p1, zz, p0);
+                    p0 = cmk<double>(fma(p0.re, zz.re, fma(-p0.im, zz.im, a_s[j * T + tid])), fma(p0.re, zz.im, p0.im * zz.re));
+                }
+                if (cnorm_sqr(p1) == 0.0) break;
+                zz = csub(zz, cdiv(p0, p1));
+            }
+        }
+        double fr_, bw_;
+        if (cand && from_root_f64(zz.re, zz.im, Q.fs, Q.strict_im != 0, &fr_, &bw_)) {
+            st_s[cnt * T + tid] = fr_;
+            st_s[(P / 2 + 1 + cnt) * T + tid] = bw_;
+            ++cnt;
+        }
+    }
+    if (Q.status_out) Q.status_out[f] = VBX_OK;
+    if (Q.nres_out) Q.nres_out[f] = cnt;
+    if (Q.res_out) {
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const double fk = st_s[k * T + tid];
+            int rank = 0;
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                const double fj = st_s[j * T + tid];
+                rank += (fj < fk || (fj == fk && j < k)) ? 1 : 0;
+            }
+            if (rank < R) write_res(rank, fk, st_s[(P / 2 + 1 + k) * T + tid]);
+        }
+        for (int s = cnt; s < R; ++s) write_res(s, 0.0, 0.0);
+    }
+}
+
+static inline size_t roots_pair_smem_bytes(int P) {
+    // a_s [P+1] f64, st_s [P+2] f64 (frequencies in rows 0..P/2, bandwidths in rows P/2+1..P+1), r_s [P] complex f32, c_s [P+1] f32
+    return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)(P + 2) * 8 + (size_t)P * 8 + (size_t)(P + 1) * 4);
+}
+
 static inline size_t roots_rt_smem_bytes(int P, bool f32) {
     const size_t cs = f32 ? 8 : 16;
     return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)(P + 1) * cs + (size_t)P * cs);
