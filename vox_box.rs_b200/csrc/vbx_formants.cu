@@ -249,7 +249,7 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
     // fp32 path without a request for the roots themselves: conjugate-pair deflation (vbx_roots_kernel.cuh); VBX_ROOTS_PAIR=0
     // keeps the reference's one-root-at-a-time order for A/B runs
     const char* pe = getenv("VBX_ROOTS_PAIR");
-    if (f32 && !Q.roots_out && (pe && pe[0] == '1')) {  // opt-in until validated on the GPU
+    if (f32 && !Q.roots_out && !(pe && pe[0] == '0')) {
         const size_t smem_pair = roots_pair_smem_bytes(p);
         VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
         lpc_roots_pair_kernel<<<(unsigned)grid, kRootsThreads, smem_pair, ctx->stream>>>(Q, p);
