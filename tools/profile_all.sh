@@ -11,7 +11,7 @@ full() { # name regex command...
 }
 full lpc16 lpc_fused16 python bench.py --config c2 --steps 1 --warmup 0 --no-cpu
 full lpc "lpc_fused_kernel" python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
-full roots lpc_roots_rt python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
+full roots lpc_roots_ python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
 full tracker tracker_idx python bench.py --config c3 --utts 1125 --steps 1 --warmup 0 --no-cpu
 full lag pitch_lag python bench.py --config c4 --utts 48 --steps 1 --warmup 0 --no-cpu
 full refine pitch_refine8 python bench.py --config c4 --utts 48 --steps 1 --warmup 0 --no-cpu
