@@ -275,8 +275,12 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     typedef float TR;
     const unsigned FULL = 0xffffffffu;
     double* a_s = reinterpret_cast<double*>(roots_smem);                    // [P+1][T] original real coefficients
-    double* st_s = a_s + (size_t)(P + 1) * T;                               // [P+2][T] staged frequencies (rows 0..P/2) | bandwidths
-    vcx<TR>* r_s = reinterpret_cast<vcx<TR>*>(st_s + (size_t)(P + 2) * T);  // [P][T]   roots (im >= 0 first of a pair)
+    vcx<TR>* r_s = reinterpret_cast<vcx<TR>*>(a_s + (size_t)(P + 1) * T);   // [P][T]   roots (im >= 0 first of a pair)
+    // The sorted-resonance staging reuses the root rows as they are consumed: an 8-byte row holds one double, resonance i
+    // goes to rows 2i (frequency) and 2i+1 (bandwidth).  Candidate k (im > 0) sits right before its conjugate and at most
+    // floor(k / 2) resonances precede it, so rows 2i and 2i+1 <= k + 1 are the candidate's own (already in registers) and
+    // its conjugate's (skipped by the loop) or older.
+    double* st_s = reinterpret_cast<double*>(r_s);
     float* c_s = reinterpret_cast<float*>(r_s + (size_t)P * T);             // [P+1][T] working polynomial (real)
     const int tid = threadIdx.x;
     const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
@@ -419,9 +423,11 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
             }
         }
         double fr_, bw_;
-        if (cand && from_root_f64(zz.re, zz.im, Q.fs, Q.strict_im != 0, &fr_, &bw_)) {
-            st_s[cnt * T + tid] = fr_;
-            st_s[(P / 2 + 1 + cnt) * T + tid] = bw_;
+        const bool keep = cand && from_root_f64(zz.re, zz.im, Q.fs, Q.strict_im != 0, &fr_, &bw_);
+        if (zr.im > (TR)0) ++k;  // the next row is this root's conjugate (never a candidate): skip it — it may be overwritten below
+        if (keep) {
+            st_s[(2 * cnt) * T + tid] = fr_;
+            st_s[(2 * cnt + 1) * T + tid] = bw_;
             ++cnt;
         }
     }
@@ -430,22 +436,22 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     if (Q.res_out) {
 #pragma unroll 1
         for (int k = 0; k < cnt; ++k) {
-            const double fk = st_s[k * T + tid];
+            const double fk = st_s[(2 * k) * T + tid];
             int rank = 0;
 #pragma unroll 1
             for (int j = 0; j < cnt; ++j) {
-                const double fj = st_s[j * T + tid];
+                const double fj = st_s[(2 * j) * T + tid];
                 rank += (fj < fk || (fj == fk && j < k)) ? 1 : 0;
             }
-            if (rank < R) write_res(rank, fk, st_s[(P / 2 + 1 + k) * T + tid]);
+            if (rank < R) write_res(rank, fk, st_s[(2 * k + 1) * T + tid]);
         }
         for (int s = cnt; s < R; ++s) write_res(s, 0.0, 0.0);
     }
 }
 
 static inline size_t roots_pair_smem_bytes(int P) {
-    // a_s [P+1] f64, st_s [P+2] f64 (frequencies in rows 0..P/2, bandwidths in rows P/2+1..P+1), r_s [P] complex f32, c_s [P+1] f32
-    return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)(P + 2) * 8 + (size_t)P * 8 + (size_t)(P + 1) * 4);
+    // a_s [P+1] f64, r_s [P] complex f32 (reused as the resonance staging), c_s [P+1] f32
+    return (size_t)kRootsThreads * ((size_t)(P + 1) * 8 + (size_t)P * 8 + (size_t)(P + 1) * 4);
 }
 
 static inline size_t roots_rt_smem_bytes(int P, bool f32) {
