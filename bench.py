@@ -410,6 +410,9 @@ class Workload:
                 "lpc_fused_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), "r1_lpc_final_full.txt"),
                 "lpc_fused16_kernel": ("fp64", 2 * (p + 1) * N + N + 350, 4 * hop + 8 * (p + 1), "r1_lpc16_final_full.txt"),
                 # 10 Laguerre solves x 20 iterations x (3*12 complex FMA*8 + ~60) + polish/resonances ~ 70 k flop (fp32 pipe)
+                # (SURVEY §8d counts the REFERENCE's algorithm: one root at a time.  The kernel that runs divides conjugate
+                # pairs out and executes roughly half of these flops, so this fraction is work-equivalent, not pipe utilisation:
+                # ncu reads 34 % FMA-pipe / 67 % issue utilisation, profiles/r1_roots_final_full.txt.)
                 "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt"),
                 "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_final_full.txt"),
             },
@@ -436,6 +439,9 @@ class Workload:
                 sec = ms * 1e-3 / steps
                 entry.update({"bound": pipe, "tflops": flop * self.F / sec / 1e12, "frac": flop * self.F / sec / 1e12 / peaks[pipe + "_tflops"],
                               "gbs": byts * self.F / sec / 1e9, "frac_hbm": byts * self.F / sec / 1e9 / hbm_peak})
+                if name == "lpc_roots_rt_kernel":
+                    entry["note"] = ("flops counted for the reference's one-root-at-a-time algorithm (SURVEY 8d); the conjugate-pair "
+                                     "kernel executes about half of them: work-equivalent rate, not pipe utilisation")
             kernels[name] = entry
         dom = next((k for k in kernels if k in table), None)
         if dom is None:
