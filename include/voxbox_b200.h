@@ -206,8 +206,9 @@ VBX_API int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dty
  * lpc: [F][lpc_stride], either [1, a1..ap] (lpc_has_leading_one = 1, Levinson's `ac`) or [a1..ap] (Burg).
  * precision: 0 = fp32 Laguerre/deflation + fp64 Newton polish on the original polynomial (default), 1 = fp64
  * Laguerre/deflation as the reference's f64 instantiation, -1 = library default (env VBX_ROOTS_F64=1 selects 1).
- * roots_out (optional): [F][p] complex roots in find_roots order.  status_in (optional): frames whose LPC stage
- * failed are passed through with zero resonances. */
+ * roots_out (optional): [F][p] complex roots in find_roots order; without it the fp32 path divides conjugate pairs
+ * out of the (real) polynomial instead of one root at a time — same resonances, no root list.  status_in
+ * (optional): frames whose LPC stage failed are passed through with zero resonances. */
 VBX_API int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride,
                                   int32_t p, int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im,
                                   const uint8_t* status_in, void* res_out, int32_t res_slots, int32_t* nres_out,
