@@ -232,6 +232,28 @@ def test_find_formants_synthetic_utterances(oracle, fs, N, hop, method, window):
     assert worst_res < 1e-3  # fp64-polished roots: far inside the tolerance
 
 
+@pytest.mark.parametrize("fs,N,hop", [(16000, 400, 160), (44100, 1102, 441)])
+@pytest.mark.parametrize("p", [3, 4, 8, 11, 12, 13, 16])
+def test_pair_deflation_matches_one_at_a_time(fs, N, hop, p):
+    """The fused fp32 path divides conjugate pairs out of the real LPC polynomial (lpc_roots_pair_kernel); a call that asks
+    for the roots keeps the reference's one-root-at-a-time order (lpc_roots_rt_kernel).  Same polynomial, same fp64
+    polish: the resonances must be the same set — identical counts, values far inside the 0.5 Hz tolerance — for even and
+    odd orders (an odd order has at least one real root: the linear-factor branch), both `im` filters, Levinson and Burg."""
+    audio = synth.utterance(31 + p, fs, seconds=2.0)
+    c = ctx()
+    F = c.n_frames_of(audio.size, N, hop)
+    d = c.to_device(audio)
+    _, ac, _ = c.lpc(c.frames(d.ptr, F, N, hop, vb.WINDOW_HANN_SYMMETRIC), p)
+    burg, _ = c.lpc_burg(c.frames(d.ptr, F, N, hop, vb.WINDOW_HANN_PERIODIC), p)
+    for lpc, has_one in ((ac, True), (burg, False)):
+        for strict in (True, False):
+            a = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict)                    # pair deflation
+            b = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict, want_roots=True)   # one at a time
+            assert np.array_equal(a["status"].to_host(), b["status"].to_host())
+            assert np.array_equal(a["n_res"].to_host(), b["n_res"].to_host()), (has_one, strict)
+            assert np.max(np.abs(a["resonances"].to_host() - b["resonances"].to_host())) < 1e-2, (has_one, strict)
+
+
 def test_roots_precisions_agree(oracle):
     """fp32 Laguerre + fp64 polish (default) and the fp64 Laguerre path give the same resonances."""
     audio = synth.utterance(9, 16000, seconds=2.0)
