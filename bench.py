@@ -412,7 +412,7 @@ class Workload:
                 # 10 Laguerre solves x 20 iterations x (3*12 complex FMA*8 + ~60) + polish/resonances ~ 70 k flop (fp32 pipe)
                 # (SURVEY §8d counts the REFERENCE's algorithm: one root at a time.  The kernel that runs divides conjugate
                 # pairs out and executes roughly half of these flops, so this fraction is work-equivalent, not pipe utilisation:
-                # ncu reads 34 % FMA-pipe / 67 % issue utilisation, profiles/r1_roots_final_full.txt.)
+                # ncu reads 39 % FMA-pipe / 81 % issue utilisation, profiles/r1_roots_final_full.txt.)
                 "lpc_roots_rt_kernel": ("fp32", 70e3, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt"),
                 "tracker_idx_kernel": ("fp64", 600.0, 8 * p + 4 + 4 * 8, "r1_tracker_final_full.txt"),
             },
