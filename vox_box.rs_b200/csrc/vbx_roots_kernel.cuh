@@ -335,7 +335,11 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
             } else {
                 const vcx<TR> step = laguerre_step<TR, true>(a0, a1, a2, nn, nref);
                 z = cadd(z, step);
-                const TR eps = (TR)3.0e-7;
+                // Laguerre converges cubically: a step of 1e-5·|z| means the iterate is already exact to fp32, and the fp64
+                // polish that follows squares whatever error is left twice.  (3e-7, the fp32 rounding level, made solves
+                // jitter around the threshold for extra iterations: 20 % more Horner work for the same roots; 1e-3 is where
+                // resonance counts start to differ — numpy emulation of this kernel, 16 and 44.1 kHz.)
+                const TR eps = (TR)1.0e-5;
                 if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) done = true;
                 if (++it == 20) done = true;
             }
