@@ -233,7 +233,7 @@ def test_find_formants_synthetic_utterances(oracle, fs, N, hop, method, window):
 
 
 @pytest.mark.parametrize("fs,N,hop", [(16000, 400, 160), (44100, 1102, 441)])
-@pytest.mark.parametrize("p", [3, 4, 8, 11, 12, 13, 16])
+@pytest.mark.parametrize("p", [2, 3, 4, 8, 11, 12, 13, 16, 24])
 def test_pair_deflation_matches_one_at_a_time(fs, N, hop, p):
     """The fused fp32 path divides conjugate pairs out of the real LPC polynomial (lpc_roots_pair_kernel); a call that asks
     for the roots keeps the reference's one-root-at-a-time order (lpc_roots_rt_kernel).  Same polynomial, same fp64
@@ -247,11 +247,18 @@ def test_pair_deflation_matches_one_at_a_time(fs, N, hop, p):
     burg, _ = c.lpc_burg(c.frames(d.ptr, F, N, hop, vb.WINDOW_HANN_PERIODIC), p)
     for lpc, has_one in ((ac, True), (burg, False)):
         for strict in (True, False):
-            a = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict)                    # pair deflation
-            b = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict, want_roots=True)   # one at a time
-            assert np.array_equal(a["status"].to_host(), b["status"].to_host())
-            assert np.array_equal(a["n_res"].to_host(), b["n_res"].to_host()), (has_one, strict)
-            assert np.max(np.abs(a["resonances"].to_host() - b["resonances"].to_host())) < 1e-2, (has_one, strict)
+            a = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict)                    # pair deflation, fp32 + polish
+            b = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict, want_roots=True)   # one at a time, fp32 + polish
+            t = c.lpc_to_resonances(lpc, p, has_one, float(fs), strict_im=strict, want_roots=True, precision=1)  # one at a time, fp64
+            for x in (a, b):
+                assert np.array_equal(x["status"].to_host(), t["status"].to_host())
+                assert np.array_equal(x["n_res"].to_host(), t["n_res"].to_host()), (has_one, strict)
+            # against the fp64 path: the pair kernel (real-coefficient deflation) stays at rounding level even at order 24,
+            # where the fp32 one-at-a-time deflation with complex coefficients drifts by 0.05 Hz at 16 kHz and 1.6 Hz at
+            # 44.1 kHz (a caller who wants the root list at such orders asks for precision = 1)
+            assert np.max(np.abs(a["resonances"].to_host() - t["resonances"].to_host())) < 1e-3, (has_one, strict)
+            if p <= 16:
+                assert np.max(np.abs(b["resonances"].to_host() - t["resonances"].to_host())) < 0.5, (has_one, strict)
 
 
 def test_roots_precisions_agree(oracle):
