@@ -74,7 +74,9 @@ typedef enum vbx_window {
  * A batch of equally long utterances is a two-level view: with frames_per_segment = J > 0, frame
  * f = u*J + j starts at base[u*segment_stride + j*frame_stride] (n_frames must be a multiple of J);
  * frames_per_segment == 0 means one segment holds all frames.
- * dtype: VBX_F32 samples, or VBX_I16 PCM scaled by 1/32767 on load (tests/lib.rs:17-19). */
+ * dtype: VBX_F32 samples, VBX_I16 PCM scaled by 1/32767 on load (tests/lib.rs:17-19), or VBX_F64 samples (what the
+ * reference's f64 callers hold, e.g. a frame they windowed themselves: use VBX_WINDOW_NONE; f64 samples run the same
+ * arithmetic through the general-purpose kernels, the tuned batch kernels stage fp32 / int16). */
 typedef struct vbx_frames {
     const void* base;
     int64_t n_frames;
@@ -82,7 +84,7 @@ typedef struct vbx_frames {
     int64_t frames_per_segment; /* J, or 0 */
     int64_t segment_stride;     /* in samples; ignored when frames_per_segment == 0 */
     int32_t frame_len;          /* N */
-    int32_t dtype;        /* vbx_dtype: VBX_F32 or VBX_I16 */
+    int32_t dtype;        /* vbx_dtype: VBX_F32, VBX_I16 or VBX_F64 */
     int32_t window;       /* vbx_window */
     int32_t reserved;     /* must be 0 */
 } vbx_frames;
@@ -135,6 +137,13 @@ VBX_API int vbx_profile_begin(vbx_ctx* ctx);
 VBX_API int vbx_profile_end(vbx_ctx* ctx);
 VBX_API int vbx_profile_count(vbx_ctx* ctx);
 VBX_API int vbx_profile_entry(vbx_ctx* ctx, int index, char* name_out, int name_len, double* ms_total, int64_t* launches);
+
+/* Executed-work counters of the data-dependent kernels, accumulated between vbx_profile_begin and vbx_profile_end (zero
+ * outside): out[0] = Horner coefficient steps and out[1] = Laguerre rounds executed by lpc_roots_pair_kernel, summed over
+ * lanes (a warp runs every round at its largest live degree, so idle lanes' steps are counted: executed, not useful, work);
+ * out[2] = term-loop iterations and out[3] = interpolant evaluations executed by pitch_refine8q_kernel, summed over lanes.
+ * bench.py turns them into executed flop for the roofline fractions of those kernels.  Synchronises.  n <= 8. */
+VBX_API int vbx_profile_counters(vbx_ctx* ctx, uint64_t* out, int32_t n);
 
 /* Measured pipe peaks of this device (dependent-free FMA loops on every SM), used as roofline
  * denominators for the FP32/FP64-bound kernels.  Values in TFLOP/s (2 flop per FMA). */
@@ -328,6 +337,53 @@ VBX_API int vbx_preemphasis(vbx_ctx* ctx, void* x_inout, int32_t dtype, int64_t 
 VBX_API int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
                                         int32_t n_coeffs, void* est_inout, int32_t n_formants, void* tracks_out,
                                         void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
+
+/* The same call with the reference's literal buffer semantics (lib.rs:54,62-75): find_formants windows and analyses
+ * its WHOLE `resampled_buf`, not just the first resampled_len = ceil(resample_ratio * frame_len) entries it fills.  With
+ * resampled_buf_len > resampled_len (tests/lib.rs:59,66: buf.len() = 1024, resampled_buf.len() = 2878) every frame is the resampled
+ * (or, for ratio 1, copied) samples followed by the buffer's untouched tail — zeros, as in the reference's tests — the periodic
+ * Hann runs at phase idx / resampled_len over the whole buffer and Burg sees resampled_buf_len samples.  resampled_buf_len = 0
+ * means resampled_len (vbx_find_formants_resampled); a value below resampled_len is VBX_ERR_BADARG (the reference's assert!). */
+VBX_API int vbx_find_formants_buffered(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
+                                       int64_t resampled_buf_len, int32_t n_coeffs, void* est_inout, int32_t n_formants,
+                                       void* tracks_out, void* resonances_out, int32_t* nres_out, uint8_t* status_out,
+                                       int32_t dtype);
+
+/* ---- the whole box behind one handle (utterance sharding, no collective, host-side gather) ---------------------------
+ * The reference is single-threaded CPU code; its callers loop over utterances.  vbx_multi owns one worker thread + one vbx_ctx per
+ * device; a `_multi_host` call splits the caller's view into contiguous ranges of segments (utterances; vbx_multi_partition's
+ * rule) — or of frames when the view is a single segment and the path is stateless — runs the ordinary `_host` pipeline of every
+ * range on its device concurrently, and returns when all results are in the caller's (single) host buffers at their rows: the
+ * host-side gather.  Workers bind to the CPUs local to their GPU (sysfs local_cpulist; VBX_MULTI_NO_BIND=1 disables).  No torch,
+ * NCCL or MPI is involved.  Arguments are those of the single-device `_host` twin. */
+typedef struct vbx_multi vbx_multi;
+VBX_API int vbx_multi_create(int32_t n_devices /* 0 = all visible */, const int32_t* devices /* NULL = 0..n-1 */, vbx_multi** out);
+VBX_API int vbx_multi_destroy(vbx_multi* m);
+VBX_API int32_t vbx_multi_device_count(vbx_multi* m);
+VBX_API vbx_ctx* vbx_multi_ctx(vbx_multi* m, int32_t index);   /* device `index`'s context (owned by the handle) */
+VBX_API const char* vbx_multi_last_error(vbx_multi* m);
+VBX_API int64_t vbx_multi_kernel_launches(vbx_multi* m);       /* kernels launched by all devices so far */
+/* range [lo, hi) of `n_units` that part `part` of `n_parts` owns: lo = floor(n_units * part / n_parts) */
+VBX_API void vbx_multi_partition(int64_t n_units, int32_t n_parts, int32_t part, int64_t* lo, int64_t* hi);
+VBX_API int vbx_multi_lpc_host(vbx_multi* m, const vbx_frames* frames, int32_t p, void* r_out, void* ac_out, void* kc_out,
+                               int32_t out_dtype);
+VBX_API int vbx_multi_find_formants_host(vbx_multi* m, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
+                                         int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
+                                         void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype);
+VBX_API int vbx_multi_pitch_host(vbx_multi* m, const vbx_frames* frames, double sample_rate, double threshold, double min_hz,
+                                 double max_hz, int32_t max_candidates, void* cand_out, int32_t* n_cand_out,
+                                 uint8_t* status_out, int32_t out_dtype);
+VBX_API int vbx_multi_mfcc_host(vbx_multi* m, const vbx_frames* frames, int32_t num_coeffs, int32_t n_keep, double freq_lo,
+                                double freq_hi, double sample_rate, void* out, int32_t out_dtype);
+/* Host->device copy bandwidth (GB/s per device, gbs_out[n_devices]) with the first n_active devices copying concurrently from
+ * pinned buffers allocated by their own worker threads: which link saturates as more GPUs stage at once (tools/h2d_probe.py). */
+VBX_API int vbx_multi_h2d_bandwidth(vbx_multi* m, size_t bytes_per_device, int32_t reps, int32_t n_active, double* gbs_out);
+
+/* ---- synthetic speech-like audio, generated on the device (bench / parity-at-scale infrastructure) ----------------
+ * out: [n_utts][n_samples] of dtype (VBX_F32, or VBX_I16 = the same samples as 16-bit PCM, round(x * 32767)).  Utterance u of the
+ * call is global utterance first_utt + u: a function of (seed, first_utt + u, sample_rate) only.  Recipe: csrc/vbx_synth.cu. */
+VBX_API int vbx_synth_speech(vbx_ctx* ctx, void* out, int32_t dtype, int64_t n_utts, int64_t n_samples, double sample_rate,
+                             uint64_t seed, int64_t first_utt);
 
 #ifdef __cplusplus
 }

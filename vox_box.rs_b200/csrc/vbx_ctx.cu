@@ -53,6 +53,20 @@ int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes) {
     return VBX_OK;
 }
 
+int vbx_scratch_get(vbx_ctx* ctx, size_t bytes, void** out) {
+    if (ctx->sub_scratch) {
+        if (bytes > ctx->sub_scratch_bytes)
+            return vbx_fail(ctx, VBX_ERR_NOMEM, "internal: callee scratch (%zu bytes) exceeds the caller's reservation (%zu)", bytes,
+                            ctx->sub_scratch_bytes);
+        *out = ctx->sub_scratch;
+        return VBX_OK;
+    }
+    int st = vbx_arena_reserve(ctx, bytes);
+    if (st != VBX_OK) return st;
+    *out = ctx->arena;
+    return VBX_OK;
+}
+
 int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->pipe_bytes) return VBX_OK;
     VBX_CUDA(ctx, cudaDeviceSynchronize());
@@ -253,6 +267,7 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
     for (auto& kv : ctx->windows) cudaFree(kv.second);
     vbx_mfcc_cache_free(ctx);
     for (auto e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->work_counters) cudaFree(ctx->work_counters);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pipe) cudaFree(ctx->pipe);
@@ -298,10 +313,11 @@ int vbx_malloc_host(vbx_ctx* ctx, size_t bytes, void** host_out) {
     if (!ctx || !host_out) return VBX_ERR_BADARG;
     *host_out = nullptr;
     if (bytes == 0) return VBX_OK;
-    cudaError_t e = cudaMallocHost(host_out, bytes);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaHostAlloc(host_out, bytes, cudaHostAllocPortable);  // pinned for every device's copy engines (vbx_multi)
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return vbx_fail(ctx, VBX_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return vbx_fail(ctx, VBX_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     }
     return VBX_OK;
 }
@@ -349,6 +365,14 @@ int vbx_profile_begin(vbx_ctx* ctx) {
     ctx->prof_used = 0;
     ctx->prof_names.clear();
     ctx->prof_totals.clear();
+    cudaSetDevice(ctx->device);
+    if (!ctx->work_counters) {
+        if (cudaMalloc(&ctx->work_counters, VBX_N_WORK_COUNTERS * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->work_counters = nullptr;
+        }
+    }
+    if (ctx->work_counters) cudaMemsetAsync(ctx->work_counters, 0, VBX_N_WORK_COUNTERS * sizeof(unsigned long long), ctx->stream);
     ctx->prof_on = true;
     vbx_prof_mark(ctx, "begin");
     return VBX_OK;
@@ -365,6 +389,17 @@ int vbx_profile_end(vbx_ctx* ctx) {
         t.first += ms;
         t.second += 1;
     }
+    return VBX_OK;
+}
+
+int vbx_profile_counters(vbx_ctx* ctx, uint64_t* out, int32_t n) {
+    if (!ctx || !out || n < 0) return VBX_ERR_BADARG;
+    unsigned long long host[VBX_N_WORK_COUNTERS] = {0};
+    if (ctx->work_counters) {
+        VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        VBX_CUDA(ctx, cudaMemcpy(host, ctx->work_counters, sizeof(host), cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < n; ++i) out[i] = i < VBX_N_WORK_COUNTERS ? (uint64_t)host[i] : 0;
     return VBX_OK;
 }
 

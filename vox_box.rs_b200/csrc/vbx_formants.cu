@@ -199,6 +199,16 @@ template <typename TIn> burg_kernel_t pick_burg(int c_needed, int* c_out) {
     return nullptr;
 }
 
+// the block kernel keeps b1/b2 in shared memory when 2·n doubles fit (VBX_BURG_FORCE_GLOBAL=1: never, for tests)
+bool burg_block_uses_smem(const vbx_ctx* ctx, int frame_len) {
+    if (const char* e = getenv("VBX_BURG_FORCE_GLOBAL"))
+        if (e[0] == '1') return false;
+    return (size_t)2 * frame_len * sizeof(double) <= ctx->smem_optin - 1024;
+}
+bool burg_uses_warp_kernel(int frame_len) {
+    return (frame_len - 1 + 31) / 32 <= 36 && !getenv("VBX_BURG_FORCE_BLOCK") && !getenv("VBX_BURG_FORCE_GLOBAL");
+}
+
 template <typename TIn>
 int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uint8_t* status_out, int out_dtype) {
     const double* win = nullptr;
@@ -212,7 +222,7 @@ int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uin
     P.n = fr->frame_len; P.p = p; P.out_f64 = (out_dtype == VBX_F64);
     int C = 0;
     burg_kernel_t kern = pick_burg<TIn>((fr->frame_len - 1 + 31) / 32, &C);
-    if (kern && !getenv("VBX_BURG_FORCE_BLOCK")) {
+    if (kern && burg_uses_warp_kernel(fr->frame_len)) {
         const int warps = 4;
         const int64_t grid = (fr->n_frames + warps - 1) / warps;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
@@ -221,12 +231,14 @@ int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uin
         return VBX_OK;
     }
     const size_t need = (size_t)2 * fr->frame_len * sizeof(double);
-    const int use_smem = need <= ctx->smem_optin - 1024 ? 1 : 0;
+    const int use_smem = burg_block_uses_smem(ctx, fr->frame_len) ? 1 : 0;
     double* scratch = nullptr;
     if (!use_smem) {
-        st = vbx_arena_reserve(ctx, need * (size_t)fr->n_frames);
+        // global b1/b2 rows: from the caller's reservation inside vbx_find_formants (which holds arena pointers), else the arena
+        void* sp = nullptr;
+        st = vbx_scratch_get(ctx, need * (size_t)fr->n_frames, &sp);
         if (st != VBX_OK) return st;
-        scratch = reinterpret_cast<double*>(ctx->arena);
+        scratch = reinterpret_cast<double*>(sp);
     } else {
         VBX_CUDA(ctx, cudaFuncSetAttribute(burg_block_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
@@ -253,7 +265,7 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
         const size_t smem_pair = roots_pair_smem_bytes(p);
         VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
         lpc_roots_pair_kernel<<<(unsigned)grid, kRootsThreads, smem_pair, ctx->stream>>>(Q, p);
-        VBX_CHECK_LAUNCH(ctx, "lpc_roots_rt_kernel");
+        VBX_CHECK_LAUNCH(ctx, "lpc_roots_pair_kernel");
         return VBX_OK;
     }
     const size_t smem = roots_rt_smem_bytes(p, f32);
@@ -804,17 +816,28 @@ template <typename TIn>
 __global__ void __launch_bounds__(256) resample_kernel(const TIn* __restrict__ base, int64_t n_frames, int64_t stride,
                                                        int64_t seg_frames, int64_t seg_stride, int n, double scale,
                                                        const int* __restrict__ idx, const double* __restrict__ w, int rlen,
+                                                       const double* __restrict__ win /* [rlen] or null */, int row_len, int copy_only,
                                                        double* __restrict__ out) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_frames * rlen) return;
-    const int64_t f = e / rlen;
-    const int k = (int)(e - f * rlen);
+    if (e >= n_frames * row_len) return;
+    const int64_t f = e / row_len;
+    const int k = (int)(e - f * row_len);
+    if (k >= rlen) {  // the untouched tail of the reference's resampled_buf: zeros (0·window = 0)
+        out[e] = 0.0;
+        return;
+    }
     const int64_t seg = f / seg_frames;
     const TIn* x = base + seg * seg_stride + (f - seg * seg_frames) * stride;
-    const int i = __ldg(idx + k);
-    const double left = (i < n) ? vbx_load_sample_d<TIn>(x + i) * scale : 0.0;
-    const double right = (i + 1 < n) ? vbx_load_sample_d<TIn>(x + i + 1) * scale : 0.0;
-    out[e] = left + (right - left) * __ldg(w + k);
+    double v;
+    if (copy_only) {  // resample_ratio == 1: lib.rs:62-64 copies
+        v = vbx_load_sample_d<TIn>(x + k) * scale;
+    } else {
+        const int i = __ldg(idx + k);
+        const double left = (i < n) ? vbx_load_sample_d<TIn>(x + i) * scale : 0.0;
+        const double right = (i + 1 < n) ? vbx_load_sample_d<TIn>(x + i + 1) * scale : 0.0;
+        v = left + (right - left) * __ldg(w + k);
+    }
+    out[e] = win ? v * __ldg(win + k) : v;
 }
 
 int root_precision_default() {
@@ -823,6 +846,11 @@ int root_precision_default() {
 }
 
 }  // namespace
+
+size_t vbx_burg_scratch_bytes(vbx_ctx* ctx, const vbx_frames* fr) {
+    if (burg_uses_warp_kernel(fr->frame_len) || burg_block_uses_smem(ctx, fr->frame_len)) return 0;
+    return (size_t)2 * fr->frame_len * sizeof(double) * (size_t)fr->n_frames;
+}
 
 extern "C" {
 
@@ -865,6 +893,7 @@ int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int6
     Q.status_out = status_out; Q.n_frames = n_frames; Q.fs = sample_rate; Q.lpc_stride = lpc_stride;
     Q.lpc_has_one = lpc_has_leading_one ? 1 : 0; Q.lpc_f64 = (lpc_dtype == VBX_F64); Q.out_f64 = (out_dtype == VBX_F64);
     Q.R = res_slots; Q.strict_im = strict_im ? 1 : 0; Q.polish_steps = 2;
+    Q.work = vbx_work_ptr(ctx);
     return launch_lpc_roots(ctx, Q, p, precision < 0 ? root_precision_default() : precision);
 }
 
@@ -1007,7 +1036,7 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
                       void* est_inout, int32_t n_formants, void* tracks_out, void* resonances_out, int32_t* nres_out,
                       uint8_t* status_out, int32_t dtype) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/lpc_method == VBX_LPC_BURG);
+    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, lpc_method == VBX_LPC_BURG || lpc_method == VBX_LPC_AUTOCORR, "unknown lpc_method");
@@ -1027,9 +1056,18 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     const int R = own_res ? p : VBX_MAX_RESONANCES;
     const size_t res_bytes = own_res ? al((size_t)F * R * res_es) : 0;
     const size_t nres_bytes = nres_out ? 0 : al((size_t)F * sizeof(int32_t));
-    st = vbx_arena_reserve(ctx, lpc_bytes + 2 * st_bytes + res_bytes + nres_bytes);
+    // the LPC stage's own scratch (Burg rows that do not fit shared memory, the r rows of the non-fused autocorrelation
+    // path) is part of THIS reservation: a callee that grew the arena would free the block the pointers below point into
+    const size_t sub_bytes = al(lpc_method == VBX_LPC_BURG ? vbx_burg_scratch_bytes(ctx, frames) : vbx_lpc_scratch_bytes(ctx, frames, p + 1));
+    const size_t own_bytes = lpc_bytes + 2 * st_bytes + res_bytes + nres_bytes;
+    st = vbx_arena_reserve(ctx, own_bytes + sub_bytes);
     if (st != VBX_OK) return st;
     char* base = (char*)ctx->arena;
+    struct SubScratch {  // scoped: the callees of this call see the sub-range, nobody else does
+        vbx_ctx* c;
+        SubScratch(vbx_ctx* c_, void* p_, size_t b_) : c(c_) { c->sub_scratch = b_ ? p_ : nullptr; c->sub_scratch_bytes = b_; }
+        ~SubScratch() { c->sub_scratch = nullptr; c->sub_scratch_bytes = 0; }
+    };
     int32_t* d_nres = nres_out ? nres_out : (int32_t*)(base + lpc_bytes + 2 * st_bytes + res_bytes);
     double* d_lpc = (double*)base;
     uint8_t* d_st_lpc = (uint8_t*)(base + lpc_bytes);
@@ -1037,6 +1075,8 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     void* d_res = own_res ? (void*)(base + lpc_bytes + 2 * st_bytes) : resonances_out;
     const uint8_t* lpc_status = nullptr;
     int lpc_stride, has_one;
+    {
+    SubScratch sub(ctx, base + own_bytes, sub_bytes);
     if (lpc_method == VBX_LPC_BURG) {
         st = vbx_lpc_burg(ctx, frames, p, d_lpc, d_st_lpc, VBX_F64);
         lpc_status = d_st_lpc;
@@ -1046,6 +1086,7 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
         st = vbx_lpc(ctx, frames, p, nullptr, d_lpc, nullptr, VBX_F64);
         lpc_stride = p + 1;
         has_one = 1;
+    }
     }
     if (st != VBX_OK) return st;
     st = vbx_lpc_to_resonances(ctx, d_lpc, VBX_F64, F, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
@@ -1062,12 +1103,13 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
 
 }  // extern "C"
 
-// lib.rs:40-116 with resample_ratio != 1: resample every frame linearly to ceil(ratio·N) samples (f64), then the
-// reference's own chain — periodic Hann over the resampled length, Burg, roots, resonances, McCandless step.
-// frames->window must be VBX_WINDOW_NONE (find_formants windows AFTER resampling, lib.rs:66-70).
-extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
-                                           int32_t n_coeffs, void* est_inout, int32_t n_formants, void* tracks_out,
-                                           void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
+// lib.rs:40-116 with resample_ratio != 1 and / or a resampled_buf longer than the resampled frame: resample every frame
+// linearly to ceil(ratio·N) samples (f64) — or copy it (ratio 1) — into a zero-tailed row of resampled_buf_len samples, then
+// the reference's own chain: periodic Hann at phase idx / resampled_len over the whole row, Burg over the whole row, roots,
+// resonances, McCandless step.  frames->window must be VBX_WINDOW_NONE (find_formants windows AFTER resampling, lib.rs:66-70).
+extern "C" int vbx_find_formants_buffered(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
+                                          int64_t resampled_buf_len, int32_t n_coeffs, void* est_inout, int32_t n_formants,
+                                          void* tracks_out, void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
     if (!ctx) return VBX_ERR_BADARG;
     int st = vbx_check_frames(ctx, frames, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
@@ -1078,17 +1120,23 @@ extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frame
     const double rl = ceil(resample_ratio * (double)n);
     VBX_REQUIRE(ctx, rl >= 2.0 && rl <= 1.0e6, "resampled frame length out of range");
     const int rlen = (int)rl;
+    VBX_REQUIRE(ctx, resampled_buf_len == 0 || resampled_buf_len >= rlen,
+                "resampled_buf_len (%lld) < resampled_len (%d): the reference's assert!(resampled_len <= resampled_buf.len())",
+                (long long)resampled_buf_len, rlen);
+    VBX_REQUIRE(ctx, resampled_buf_len <= 1000000, "resampled_buf_len out of range");
+    const int row_len = resampled_buf_len > 0 ? (int)resampled_buf_len : rlen;
     if (F == 0) return VBX_OK;
     cudaSetDevice(ctx->device);
     vbx_frames rfr = *frames;
-    if (resample_ratio == 1.0) {  // lib.rs:62-64: plain copy
+    if (resample_ratio == 1.0 && row_len == rlen) {  // lib.rs:62-64: plain copy, window over exactly the frame
         rfr.window = VBX_WINDOW_HANN_PERIODIC;
         return vbx_find_formants(ctx, &rfr, sample_rate, n_coeffs, VBX_LPC_BURG, est_inout, n_formants, tracks_out, resonances_out,
                                  nres_out, status_out, dtype);
     }
+    const bool copy_only = (resample_ratio == 1.0);
     // the converter's stepping, sequential in f64 (sample 0.10 interpolate::Converter::next)
     std::vector<int> idx(rlen);
-    std::vector<double> w(rlen);
+    std::vector<double> w(rlen), win(rlen);
     {
         double interp = 0.0;
         const double step = 1.0 / resample_ratio;
@@ -1100,11 +1148,16 @@ extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frame
             interp += step;
         }
     }
-    // a private block: [F][rlen] f64 + the tables (the inner find_formants uses the context arena)
+    // lib.rs:66-70: window[idx] = Hanning::at_phase(idx · (1 / resampled_len)), host f64 (applied here, so the inner call sees
+    // frames that are already windowed; only needed when the row is longer than the resampled frame — otherwise the periodic
+    // Hann table of the Burg stage is the same thing)
+    const bool window_here = row_len != rlen;
+    if (window_here) vbx_window_fill_host(VBX_WINDOW_HANN_PERIODIC, rlen, win.data());
+    // a private block: [F][row_len] f64 + the tables (the inner find_formants uses the context arena)
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t out_bytes = al((size_t)F * rlen * sizeof(double)), idx_bytes = al((size_t)rlen * 4), w_bytes = al((size_t)rlen * 8);
+    const size_t out_bytes = al((size_t)F * row_len * sizeof(double)), idx_bytes = al((size_t)rlen * 4), w_bytes = al((size_t)rlen * 8);
     void* blk = nullptr;
-    cudaError_t e = cudaMalloc(&blk, out_bytes + idx_bytes + w_bytes);
+    cudaError_t e = cudaMalloc(&blk, out_bytes + idx_bytes + 2 * w_bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return vbx_fail(ctx, VBX_ERR_NOMEM, "find_formants_resampled: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -1112,28 +1165,32 @@ extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frame
     double* d_out = (double*)blk;
     int* d_idx = (int*)((char*)blk + out_bytes);
     double* d_w = (double*)((char*)blk + out_bytes + idx_bytes);
+    double* d_win = (double*)((char*)blk + out_bytes + idx_bytes + w_bytes);
     auto run = [&]() -> int {
         VBX_CUDA(ctx, cudaMemcpyAsync(d_idx, idx.data(), (size_t)rlen * 4, cudaMemcpyHostToDevice, ctx->stream));
         VBX_CUDA(ctx, cudaMemcpyAsync(d_w, w.data(), (size_t)rlen * 8, cudaMemcpyHostToDevice, ctx->stream));
-        const int64_t total = F * rlen;
+        if (window_here) VBX_CUDA(ctx, cudaMemcpyAsync(d_win, win.data(), (size_t)rlen * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t total = F * row_len;
         const int64_t grid = (total + 255) / 256;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
         const int64_t J = vbx_frames_per_segment(frames);
         const int64_t seg_stride = frames->frames_per_segment > 0 ? frames->segment_stride : 0;
+        const double* wn = window_here ? d_win : nullptr;
         if (frames->dtype == VBX_I16)
             resample_kernel<int16_t><<<(unsigned)grid, 256, 0, ctx->stream>>>((const int16_t*)frames->base, F, frames->frame_stride, J,
-                                                                           seg_stride, n, 1.0 / 32767.0, d_idx, d_w, rlen, d_out);
+                                                                           seg_stride, n, 1.0 / 32767.0, d_idx, d_w, rlen, wn, row_len,
+                                                                           copy_only, d_out);
         else if (frames->dtype == VBX_F64)
             resample_kernel<double><<<(unsigned)grid, 256, 0, ctx->stream>>>((const double*)frames->base, F, frames->frame_stride, J,
-                                                                          seg_stride, n, 1.0, d_idx, d_w, rlen, d_out);
+                                                                          seg_stride, n, 1.0, d_idx, d_w, rlen, wn, row_len, copy_only, d_out);
         else
             resample_kernel<float><<<(unsigned)grid, 256, 0, ctx->stream>>>((const float*)frames->base, F, frames->frame_stride, J,
-                                                                         seg_stride, n, 1.0, d_idx, d_w, rlen, d_out);
+                                                                         seg_stride, n, 1.0, d_idx, d_w, rlen, wn, row_len, copy_only, d_out);
         VBX_CHECK_LAUNCH(ctx, "resample_kernel");
         vbx_frames pf;
-        pf.base = d_out; pf.n_frames = F; pf.frame_stride = rlen; pf.frames_per_segment = frames->frames_per_segment;
-        pf.segment_stride = (frames->frames_per_segment > 0) ? frames->frames_per_segment * (int64_t)rlen : 0;
-        pf.frame_len = rlen; pf.dtype = VBX_F64; pf.window = VBX_WINDOW_HANN_PERIODIC; pf.reserved = 0;
+        pf.base = d_out; pf.n_frames = F; pf.frame_stride = row_len; pf.frames_per_segment = frames->frames_per_segment;
+        pf.segment_stride = (frames->frames_per_segment > 0) ? frames->frames_per_segment * (int64_t)row_len : 0;
+        pf.frame_len = row_len; pf.dtype = VBX_F64; pf.window = window_here ? VBX_WINDOW_NONE : VBX_WINDOW_HANN_PERIODIC; pf.reserved = 0;
         int s2 = vbx_find_formants(ctx, &pf, sample_rate, n_coeffs, VBX_LPC_BURG, est_inout, n_formants, tracks_out, resonances_out,
                                    nres_out, status_out, dtype);
         if (s2 != VBX_OK) return s2;
@@ -1146,13 +1203,20 @@ extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frame
     return st;
 }
 
+extern "C" int vbx_find_formants_resampled(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double resample_ratio,
+                                           int32_t n_coeffs, void* est_inout, int32_t n_formants, void* tracks_out,
+                                           void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
+    return vbx_find_formants_buffered(ctx, frames, sample_rate, resample_ratio, 0, n_coeffs, est_inout, n_formants, tracks_out,
+                                      resonances_out, nres_out, status_out, dtype);
+}
+
 // host twin of vbx_find_formants: chunked H2D / kernels / D2H pipeline over whole utterances (vbx_pipeline.cuh);
 // the tracker state travels once (in before the first chunk, out after the last)
 extern "C" int vbx_find_formants_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, int32_t n_coeffs,
                                       int32_t lpc_method, void* est_inout, int32_t n_formants, void* tracks_out,
                                       void* resonances_out, int32_t* nres_out, uint8_t* status_out, int32_t dtype) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, frames);
+    int st = vbx_check_frames(ctx, frames, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
     const int64_t F = frames->n_frames;

@@ -31,6 +31,10 @@ struct vbx_ctx {
     size_t arena_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // A caller inside the library that already holds arena pointers (vbx_find_formants) hands its callees their scratch
+    // as a sub-range of its own single reservation: while set, vbx_scratch_get serves from here and never touches the arena.
+    void* sub_scratch = nullptr;
+    size_t sub_scratch_bytes = 0;
     // host-call pipeline (vbx_pipeline.cuh): copy-in / copy-out streams, events, double-buffered device block
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -44,14 +48,26 @@ struct vbx_ctx {
     std::vector<const char*> prof_names;    // name of the launch that precedes event i+1 (event 0 = begin marker)
     size_t prof_used = 0;
     std::map<std::string, std::pair<double, int64_t>> prof_totals;  // name -> (ms, launches)
+    // executed-work counters of the data-dependent kernels (device, VBX_N_WORK_COUNTERS × u64; zeroed by vbx_profile_begin,
+    // incremented only while profiling is on): see vbx_profile_counters in the header
+    unsigned long long* work_counters = nullptr;
     vbx_mfcc_cache* mfcc_cache = nullptr;
     bool mfcc_fft_f32 = false;  // MFCC transform precision (default fp64)
 };
+
+enum { VBX_WORK_ROOTS_HORNER = 0, VBX_WORK_ROOTS_ROUNDS = 1, VBX_WORK_REFINE_TERMS = 2, VBX_WORK_REFINE_EVALS = 3, VBX_N_WORK_COUNTERS = 8 };
+// device pointer of the counter block while profiling is on, else null (kernels skip the accounting)
+static inline unsigned long long* vbx_work_ptr(vbx_ctx* ctx) { return ctx->prof_on ? ctx->work_counters : nullptr; }
 
 int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);
 void vbx_prof_mark(vbx_ctx* ctx, const char* name);        // records "launch `name` was just enqueued" (profiling on)
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
+// scratch for a kernel launcher: the caller-provided sub-range if one is set (see vbx_ctx::sub_scratch), else the arena
+int vbx_scratch_get(vbx_ctx* ctx, size_t bytes, void** out);
+// scratch the LPC stage of vbx_find_formants may ask for through vbx_scratch_get (0 when the fused kernels apply)
+size_t vbx_lpc_scratch_bytes(vbx_ctx* ctx, const vbx_frames* fr, int n_lags);
+size_t vbx_burg_scratch_bytes(vbx_ctx* ctx, const vbx_frames* fr);
 int vbx_pipe_reserve(vbx_ctx* ctx, size_t bytes);          // ensures ctx->pipe has >= bytes
 // cached device table (ones for NONE).  sample_dtype == VBX_I16 folds the PCM scale into the table: w[i] / 32767
 // (tests/lib.rs:17-19 scale every sample by 1/(i32::MAX >> 16) before any arithmetic).

@@ -14,6 +14,7 @@
 // partial sums are combined with shuffles; Levinson then runs one thread per frame out of shared
 // memory and the results leave through a coalesced store.
 #include <cstdlib>
+#include <type_traits>
 
 #include "vbx_internal.cuh"
 #include "vbx_pipeline.cuh"
@@ -334,11 +335,11 @@ __global__ void __launch_bounds__(256) autocorr_generic_kernel(const TIn* __rest
     const TIn* x = base + seg * seg_stride + (f - seg * seg_frames) * stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (use_smem) {
-        for (int i = tid; i < n; i += blockDim.x) s_x[i] = (double)vbx_load_sample<TIn>(x + i) * __ldg(win + i);
+        for (int i = tid; i < n; i += blockDim.x) s_x[i] = vbx_load_sample_d<TIn>(x + i) * __ldg(win + i);
         __syncthreads();
     }
     auto xw = [&](int i) -> double {
-        return use_smem ? s_x[i] : (double)vbx_load_sample<TIn>(x + i) * __ldg(win + i);
+        return use_smem ? s_x[i] : vbx_load_sample_d<TIn>(x + i) * __ldg(win + i);
     };
     const double x0 = xw(0);
     for (int lag = warp; lag < n_lags; lag += nwarps) {
@@ -455,7 +456,14 @@ constexpr int kMaxLevinsonOrder = 32;
 // Choose lanes-per-frame K (and the CTA size): the smallest power of two whose CTA span fits the
 // shared-memory budget, keeping each lane's part >= 2L samples.  Returns false if no fused
 // configuration fits.  VBX_LPC_PLAN="k:threads" overrides the choice (tuning experiments).
+// VBX_LPC_FORCE_GENERIC=1 (tests): no fused kernel, the generic autocorrelation + stand-alone Levinson run instead
+bool lpc_force_generic() {
+    const char* e = getenv("VBX_LPC_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
+
 bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, size_t* smem_bytes) {
+    if (lpc_force_generic()) return false;
     const int sv = (int)(stride < (int64_t)n ? stride : n);
     const int pad = ((sv & 1) == 0) ? 1 : 0;
     const size_t budget_soft = 72 * 1024;  // 3 CTAs / SM
@@ -504,7 +512,7 @@ bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, 
 // the CTA size is chosen as described in the loop below (C2: 128 threads = 64 frames, 4 CTAs / SM).
 // VBX_LPC16=0 disables the kernel, VBX_LPC16_THREADS=<n> pins the CTA size.
 bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames, int L, LpcParams* P, size_t* smem_bytes) {
-    if (L < 2 || L > kChunk || (n % kChunk) != 0) return false;
+    if (L < 2 || L > kChunk || (n % kChunk) != 0 || lpc_force_generic()) return false;
     const int sv = (int)(stride < (int64_t)n ? stride : n);
     if ((sv % kChunk) != 0) return false;
     if (const char* e = getenv("VBX_LPC16")) {
@@ -564,6 +572,12 @@ bool plan_fused16(const vbx_ctx* ctx, int n, int64_t stride, int64_t seg_frames,
 template <typename TIn>
 int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_out, void* kc_out, int out_dtype,
                bool do_levinson) {
+    const double* win = nullptr;
+    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win, fr->dtype);
+    if (st != VBX_OK) return st;
+    // f64 samples (the single-frame trait calls of the Rust shim on [f64]) take the generic kernels; the fused kernels
+    // stage fp32 / int16 samples
+    if constexpr (!std::is_same<TIn, double>::value) {
     // kernel tables: filled once, thread-safely (C++11 static initialisation)
     struct Tables {
         lpc_kernel_t general[kMaxFastLags + 1] = {nullptr};
@@ -576,9 +590,6 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     static const Tables tables;
     const lpc_kernel_t* table = tables.general;
     const lpc_kernel_t* table16 = tables.chunk16;
-    const double* win = nullptr;
-    int st = vbx_get_window(ctx, fr->window, fr->frame_len, &win, fr->dtype);
-    if (st != VBX_OK) return st;
 
     LpcParams P;
     memset(&P, 0, sizeof(P));
@@ -614,14 +625,16 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
         return VBX_OK;
     }
 
+    }
+
     // fallback: generic autocorrelation (+ stand-alone Levinson through a scratch r buffer)
     void* r_tmp = r_out;
     int r_dtype = out_dtype;
     if (do_levinson && (!r_out || out_dtype != VBX_F64)) {
-        st = vbx_arena_reserve(ctx, (size_t)fr->n_frames * L * sizeof(double));
+        st = vbx_scratch_get(ctx, (size_t)fr->n_frames * L * sizeof(double), &r_tmp);
         if (st != VBX_OK) return st;
-        r_tmp = ctx->arena;
         r_dtype = VBX_F64;
+        VBX_REQUIRE(ctx, r_tmp != ac_out && r_tmp != kc_out, "internal: the r scratch aliases an output");
     }
     const size_t xs = (size_t)fr->frame_len * sizeof(double);
     const int use_smem = xs <= ctx->smem_optin ? 1 : 0;
@@ -646,10 +659,19 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     return VBX_OK;
 }
 
+bool lpc_is_fused(vbx_ctx* ctx, const vbx_frames* fr, int L) {
+    if (fr->dtype == VBX_F64) return false;
+    LpcParams P;
+    memset(&P, 0, sizeof(P));
+    size_t smem = 0;
+    if (plan_fused16(ctx, fr->frame_len, fr->frame_stride, vbx_frames_per_segment(fr), L, &P, &smem)) return true;
+    return (L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem);
+}
+
 int lpc_dispatch(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* ac_out, void* kc_out, int out_dtype,
                  bool do_levinson) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, fr);
+    int st = vbx_check_frames(ctx, fr, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, n_lags >= 1, "n_lags must be >= 1");
@@ -660,6 +682,8 @@ int lpc_dispatch(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, vo
     cudaSetDevice(ctx->device);
     if (fr->dtype == VBX_I16)
         return launch_lpc<int16_t>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
+    if (fr->dtype == VBX_F64)
+        return launch_lpc<double>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
     return launch_lpc<float>(ctx, fr, n_lags, r_out, ac_out, kc_out, out_dtype, do_levinson);
 }
 
@@ -667,7 +691,7 @@ int lpc_dispatch(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, vo
 int lpc_host(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* ac_out, void* kc_out, int out_dtype,
              bool do_levinson) {
     if (!ctx) return VBX_ERR_BADARG;
-    int st = vbx_check_frames(ctx, fr);
+    int st = vbx_check_frames(ctx, fr, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     if (fr->n_frames == 0) return VBX_OK;
@@ -682,6 +706,12 @@ int lpc_host(vbx_ctx* ctx, const vbx_frames* fr, int n_lags, void* r_out, void* 
 }
 
 }  // namespace
+
+// scratch launch_lpc asks vbx_scratch_get for when called as vbx_lpc(.., r_out = NULL, ..) (vbx_find_formants' LPC stage)
+size_t vbx_lpc_scratch_bytes(vbx_ctx* ctx, const vbx_frames* fr, int n_lags) {
+    if (lpc_is_fused(ctx, fr, n_lags)) return 0;
+    return (size_t)fr->n_frames * n_lags * sizeof(double);
+}
 
 extern "C" {
 

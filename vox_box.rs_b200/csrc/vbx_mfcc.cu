@@ -18,6 +18,8 @@
 #include <cmath>
 #include <vector>
 
+#include <type_traits>
+
 #include "vbx_internal.cuh"
 #include "vbx_pipeline.cuh"
 
@@ -131,13 +133,13 @@ __global__ void __launch_bounds__(256) mfcc_kernel(const MfccParams P) {
         const TIn* __restrict__ x = reinterpret_cast<const TIn*>(P.base) + seg * P.seg_stride + (f - seg * P.seg_frames) * P.stride;
         if (P.mode == 0) {
             for (int i = tid; i < mc; i += nth) {
-                const TR re = (TR)((double)vbx_load_sample<TIn>(x + 2 * i) * __ldg(P.win + 2 * i));
-                const TR im = (TR)((double)vbx_load_sample<TIn>(x + 2 * i + 1) * __ldg(P.win + 2 * i + 1));
+                const TR re = (TR)(vbx_load_sample_d<TIn>(x + 2 * i) * __ldg(P.win + 2 * i));
+                const TR im = (TR)(vbx_load_sample_d<TIn>(x + 2 * i + 1) * __ldg(P.win + 2 * i + 1));
                 bufA[(size_t)q * ms + i] = mk<TR>(re, im);
             }
         } else {
             for (int i = tid; i < n; i += nth)
-                bufA[(size_t)q * ms + i] = mk<TR>((TR)((double)vbx_load_sample<TIn>(x + i) * __ldg(P.win + i)), (TR)0);
+                bufA[(size_t)q * ms + i] = mk<TR>((TR)(vbx_load_sample_d<TIn>(x + i) * __ldg(P.win + i)), (TR)0);
         }
     }
     __syncthreads();
@@ -383,7 +385,7 @@ int launch_fast_one(vbx_ctx* ctx, const mfcc_fast::FastParams& Q) {
     const int64_t cap = (int64_t)ctx->sm_count * 16;  // persistent: warps loop over frame groups
     if (grid > cap) grid = cap;
     kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(Q);
-    VBX_CHECK_LAUNCH(ctx, "mfcc_kernel");
+    VBX_CHECK_LAUNCH(ctx, "mfcc_warp_kernel");
     return VBX_OK;
 }
 
@@ -452,6 +454,8 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
     // fp32 FFT's ~1e-6 relative error then exceeds the 1e-5 norm-wise bound on quiet frames); fp32 is opt-in
     bool f32 = ctx->mfcc_fft_f32;
     if (const char* e = getenv("VBX_MFCC_FFT")) f32 = (e[0] == 'f' && e[1] == '3');
+    // (f64 samples — single windowed frames from the Rust shim's trait calls — take the generic kernel)
+    if constexpr (!std::is_same<TIn, double>::value)
     if (P.mode == 0 && !getenv("VBX_MFCC_GENERIC") && P.kmax <= n && num_coeffs <= 128 && n_keep * num_coeffs <= 2048) {
         mfcc_fast::FastParams Q;
         Q.base = P.base; Q.win = P.win; Q.tw = P.tw; Q.wu = P.wu; Q.wd = P.wd; Q.bins = P.bins; Q.items = t->items;
@@ -482,7 +486,7 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
 }
 
 int mfcc_check(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, double fs, const void* out, int out_dtype) {
-    int st = vbx_check_frames(ctx, fr);
+    int st = vbx_check_frames(ctx, fr, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, num_coeffs >= 1 && num_coeffs <= 4096, "num_coeffs must be in 1..4096");
@@ -524,6 +528,8 @@ int vbx_mfcc(vbx_ctx* ctx, const vbx_frames* frames, int32_t num_coeffs, int32_t
     cudaSetDevice(ctx->device);
     if (frames->dtype == VBX_I16)
         return launch_mfcc<int16_t>(ctx, frames, num_coeffs, n_keep, freq_lo, freq_hi, sample_rate, out, energies_out, out_dtype);
+    if (frames->dtype == VBX_F64)
+        return launch_mfcc<double>(ctx, frames, num_coeffs, n_keep, freq_lo, freq_hi, sample_rate, out, energies_out, out_dtype);
     return launch_mfcc<float>(ctx, frames, num_coeffs, n_keep, freq_lo, freq_hi, sample_rate, out, energies_out, out_dtype);
 }
 

@@ -58,6 +58,15 @@ static int vbx_run_chunked(vbx_ctx* ctx, const vbx_frames* fr, vbx_host_out* out
         ev_out[b] = ctx->ev_pipe[4 + b];
     }
     int rc = VBX_OK;
+    // a CUDA error inside the loop must not return before the drain below: copies may still touch caller memory
+#define PIPE_CUDA(call)                                                                                              \
+    {                                                                                                                \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess) {                                                                                    \
+            rc = vbx_fail(ctx, VBX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            break;                                                                                                   \
+        }                                                                                                            \
+    }
     for (int64_t c = 0; c < n_chunks && rc == VBX_OK; ++c) {
         const int b = (int)(c & 1);
         const int64_t u0 = c * units_per_chunk;
@@ -67,13 +76,13 @@ static int vbx_run_chunked(vbx_ctx* ctx, const vbx_frames* fr, vbx_host_out* out
         char* d_out = d_in + in_chunk;
         const size_t bytes_in = (size_t)((nu - 1) * unit_stride + unit_extent) * es;
         // the input buffer b is free once the compute of chunk c−2 is done
-        if (c >= 2) VBX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_comp[b], 0));
-        VBX_CUDA(ctx, cudaMemcpyAsync(d_in, (const char*)fr->base + (size_t)u0 * unit_stride * es, bytes_in,
+        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ev_comp[b], 0));
+        PIPE_CUDA(cudaMemcpyAsync(d_in, (const char*)fr->base + (size_t)u0 * unit_stride * es, bytes_in,
                                       cudaMemcpyHostToDevice, ctx->s_h2d));
-        VBX_CUDA(ctx, cudaEventRecord(ev_in[b], ctx->s_h2d));
+        PIPE_CUDA(cudaEventRecord(ev_in[b], ctx->s_h2d));
         // compute: needs its input, and its output buffer b free (D2H of chunk c−2 done)
-        VBX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[b], 0));
-        if (c >= 2) VBX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[b], 0));
+        PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in[b], 0));
+        if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out[b], 0));
         vbx_frames dfr = *fr;
         dfr.base = d_in;
         dfr.n_frames = nf;
@@ -87,20 +96,25 @@ static int vbx_run_chunked(vbx_ctx* ctx, const vbx_frames* fr, vbx_host_out* out
         }
         rc = launch(&dfr, u0 * unit_frames, segmented ? u0 : 0, outs);
         if (rc != VBX_OK) break;
-        VBX_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
-        VBX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev_comp[b], 0));
-        for (int i = 0; i < n_outs; ++i)
-            if (outs[i].host)
-                VBX_CUDA(ctx, cudaMemcpyAsync((char*)outs[i].host + (size_t)u0 * unit_frames * outs[i].bytes_per_frame, outs[i].dev,
-                                              (size_t)nf * outs[i].bytes_per_frame, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        VBX_CUDA(ctx, cudaEventRecord(ev_out[b], ctx->s_d2h));
+        PIPE_CUDA(cudaEventRecord(ev_comp[b], ctx->stream));
+        PIPE_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ev_comp[b], 0));
+        for (int i = 0; i < n_outs && rc == VBX_OK; ++i) {
+            if (!outs[i].host) continue;
+            const cudaError_t ec = cudaMemcpyAsync((char*)outs[i].host + (size_t)u0 * unit_frames * outs[i].bytes_per_frame, outs[i].dev,
+                                                   (size_t)nf * outs[i].bytes_per_frame, cudaMemcpyDeviceToHost, ctx->s_d2h);
+            if (ec != cudaSuccess) rc = vbx_fail(ctx, VBX_ERR_CUDA, "host pipeline: D2H copy failed: %s", cudaGetErrorString(ec));
+        }
+        if (rc != VBX_OK) break;
+        PIPE_CUDA(cudaEventRecord(ev_out[b], ctx->s_d2h));
     }
     // drain all three streams (also on error, so that no copy is still touching caller memory)
-    cudaStreamSynchronize(ctx->s_h2d);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->s_d2h);
+#undef PIPE_CUDA
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    const cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
     if (rc == VBX_OK) {
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "host pipeline failed: %s", cudaGetErrorString(e));
     }
     return rc;

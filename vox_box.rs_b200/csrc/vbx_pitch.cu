@@ -25,6 +25,7 @@
 //   pitch_finalize_kernel a warp per frame appends the unvoiced candidate, checks for NaN
 //                         strengths and rank-sorts by strength (stable, descending).
 #include <cmath>
+#include <type_traits>
 
 #include "vbx_internal.cuh"
 #include "vbx_pipeline.cuh"
@@ -48,6 +49,7 @@ struct PitchParams {
     double2* refined;       // [S·cap] (frequency, strength) per work-list entry
     int2* range;            // [S] (first list entry, count) per frame
     unsigned long long* counter;  // [0] number of list entries, [1] tile cursor of the refine kernel
+    unsigned long long* work;     // executed-work counters (vbx_profile_counters) or null
     int64_t frame0;         // first frame of this slab inside the batch
     int64_t n_frames;       // frames in this slab
     int64_t stride, seg_frames, seg_stride;
@@ -66,6 +68,73 @@ __device__ __forceinline__ int word_addr(int w) { return w + 4 * (w >> 4); }
 __device__ __forceinline__ int lag_steps(int n, int g) {  // 8-sample steps lag group g needs
     const int len = n - 16 * g;
     return len > 0 ? (len + 7) >> 3 : 0;
+}
+
+// Per frame (one warp), shared by the fp32 and fp64 sweeps: normalise, ÷ lag window, local maxima, parabolic, filter.
+// `smem` = the CTA's frame buffers (dead after the sweep), `frame_bytes` apart.
+__device__ __forceinline__ void pitch_lag_post(const PitchParams& P, unsigned char* smem, size_t frame_bytes, int64_t f_first, int nf) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int n = P.n;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const unsigned FULL = 0xffffffffu;
+    for (int qf = warp; qf < nf; qf += nwarps) {
+        double* yrow = P.y + (size_t)(f_first + qf) * n;
+        // waves.rs:39-59 max_amplitude: fold from |r[0]| with `>`: a NaN at index 0 sticks, later NaNs never win
+        double pm = -1.0;
+        for (int i = 1 + lane; i < n; i += 32) {
+            const double a = fabs(yrow[i]);
+            if (a > pm) pm = a;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double o = __shfl_xor_sync(FULL, pm, m);
+            if (o > pm) pm = o;
+        }
+        const double r0a = fabs(yrow[0]);
+        const double mx = (r0a != r0a) ? r0a : (pm > r0a ? pm : r0a);
+        const double scale = 1.0 / mx;  // waves.rs:70: no zero guard
+        for (int i = lane; i < n; i += 32) yrow[i] = (yrow[i] * scale) / __ldg(P.lagwin + i);
+        __syncwarp();
+        // periodic.rs:417-439: maxima of y[0..ixmax), parabolic frequency, (min, max) filter
+        const int ixmax = P.ixmax;
+        const double offset = -(double)ixmax - 1.0;
+        // one pass: the start abscissae are parked in the frame's (now dead) sample buffer, the frame's slice of the
+        // work list is reserved once the count is known, then the entries are written out
+        double* stage = reinterpret_cast<double*>(smem + (size_t)qf * frame_bytes);  // frame_bytes >= (ixmax/2 + 1)·8
+        int k = 0;
+        for (int base = 1; base + 1 < ixmax; base += 32) {
+            const int cidx = base + lane;
+            bool keep = false;
+            double nn = 0.0;
+            if (cidx + 1 < ixmax) {
+                const double peak = yrow[cidx], rev = yrow[cidx - 1], fwd = yrow[cidx + 1];
+                if (rev < peak && fwd < peak) {
+                    const double dr = 0.5 * (fwd - rev);
+                    const double d2r = 2. * peak - (rev - fwd);  // sign quirk, periodic.rs:424
+                    const double freq = P.fs / ((double)cidx + dr / d2r);
+                    keep = (freq == 0.) || (freq > P.fmin && freq < P.fmax);
+                    nn = P.fs / freq - offset;
+                }
+            }
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (keep) stage[k + __popc(bal & ((1u << lane) - 1u))] = nn;
+            k += __popc(bal);
+        }
+        const int count = k;
+        unsigned long long pos = 0;
+        if (lane == 0) {
+            pos = atomicAdd(P.counter, (unsigned long long)count);
+            P.range[f_first + qf] = make_int2((int)pos, count);
+        }
+        const int start = (int)__shfl_sync(FULL, pos, 0);  // also orders the staging writes before the reads below
+        for (int i = lane; i < count; i += 32) {
+            PitchCand e;
+            e.frame = (int)(f_first + qf);
+            e.k = i;
+            e.n = stage[i];
+            P.list[(size_t)start + i] = e;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -179,68 +248,10 @@ __global__ void __launch_bounds__(512) pitch_lag_kernel(const PitchParams P) {
     }
     __syncthreads();
 
-    // ---- per frame (one warp): normalise, ÷ lag window, local maxima, parabolic, filter ---------------------
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const unsigned FULL = 0xffffffffu;
-    for (int qf = warp; qf < nf; qf += nwarps) {
-        double* yrow = P.y + (size_t)(f_first + qf) * n;
-        // waves.rs:39-59 max_amplitude: fold from |r[0]| with `>`: a NaN at index 0 sticks, later NaNs never win
-        double pm = -1.0;
-        for (int i = 1 + lane; i < n; i += 32) {
-            const double a = fabs(yrow[i]);
-            if (a > pm) pm = a;
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            const double o = __shfl_xor_sync(FULL, pm, m);
-            if (o > pm) pm = o;
-        }
-        const double r0a = fabs(yrow[0]);
-        const double mx = (r0a != r0a) ? r0a : (pm > r0a ? pm : r0a);
-        const double scale = 1.0 / mx;  // waves.rs:70: no zero guard
-        for (int i = lane; i < n; i += 32) yrow[i] = (yrow[i] * scale) / __ldg(P.lagwin + i);
-        __syncwarp();
-        // periodic.rs:417-439: maxima of y[0..ixmax), parabolic frequency, (min, max) filter
-        const int ixmax = P.ixmax;
-        const double offset = -(double)ixmax - 1.0;
-        // one pass: the start abscissae are parked in the frame's (now dead) sample buffer, the frame's slice of the
-        // work list is reserved once the count is known, then the entries are written out
-        double* stage = reinterpret_cast<double*>(xs_all + (size_t)qf * P.xs_words);  // xs_words·4 bytes >= (ixmax/2 + 1)·8
-        int k = 0;
-        for (int base = 1; base + 1 < ixmax; base += 32) {
-            const int cidx = base + lane;
-            bool keep = false;
-            double nn = 0.0;
-            if (cidx + 1 < ixmax) {
-                const double peak = yrow[cidx], rev = yrow[cidx - 1], fwd = yrow[cidx + 1];
-                if (rev < peak && fwd < peak) {
-                    const double dr = 0.5 * (fwd - rev);
-                    const double d2r = 2. * peak - (rev - fwd);  // sign quirk, periodic.rs:424
-                    const double freq = P.fs / ((double)cidx + dr / d2r);
-                    keep = (freq == 0.) || (freq > P.fmin && freq < P.fmax);
-                    nn = P.fs / freq - offset;
-                }
-            }
-            const unsigned bal = __ballot_sync(FULL, keep);
-            if (keep) stage[k + __popc(bal & ((1u << lane) - 1u))] = nn;
-            k += __popc(bal);
-        }
-        const int count = k;
-        unsigned long long pos = 0;
-        if (lane == 0) {
-            pos = atomicAdd(P.counter, (unsigned long long)count);
-            P.range[f_first + qf] = make_int2((int)pos, count);
-        }
-        const int start = (int)__shfl_sync(FULL, pos, 0);  // also orders the staging writes before the reads below
-        for (int i = lane; i < count; i += 32) {
-            PitchCand e;
-            e.frame = (int)(f_first + qf);
-            e.k = i;
-            e.n = stage[i];
-            P.list[(size_t)start + i] = e;
-        }
-    }
+    pitch_lag_post(P, reinterpret_cast<unsigned char*>(xs_all), (size_t)P.xs_words * sizeof(float), f_first, nf);
 }
+
+#include "vbx_pitch_lag64.cuh"
 
 // -------------------------------------------------------------------------------------------
 // windowed-sinc interpolation, one warp per evaluation (periodic.rs:29-87)
@@ -633,6 +644,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
     const double EPS = 2.220446049250313e-16, sqrt_epsilon = 1.4901161193847656e-08, tol = 1e-10;
     const double sgn = (l8 & 1) ? -1.0 : 1.0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    unsigned work_terms = 0, work_evals = 0;  // executed term-loop iterations / evaluation rounds of this warp
 
     // tiles are handed out dynamically (P.counter[1]): the grid is exactly the resident CTAs and none of them idles
     // while another still has a backlog
@@ -644,7 +656,13 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
     }
     __syncthreads();
     const long long tile0 = s_tile * kRefineTile;
-    if (tile0 >= total) break;
+    if (tile0 >= total) {
+        if (P.work && lane == 0) {  // warp-uniform counts, summed over lanes
+            atomicAdd(P.work + 2, 32ULL * work_terms);
+            atomicAdd(P.work + 3, 32ULL * work_evals);
+        }
+        break;
+    }
     const int tcnt = (int)min((long long)kRefineTile, total - tile0);
     for (int i = threadIdx.x; i < tcnt; i += blockDim.x) s_key[i] = (float)P.list[tile0 + i].n;
     __syncthreads();
@@ -748,6 +766,8 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
             const double Kl = 2.0 * C8l, Kr = 2.0 * C8r, Cl = 1.0 - C8l, Cr = 1.0 - C8r;
             const int L = offset + nr, R = offset + nl;
             const int Dmax = __reduce_max_sync(FULL, D);
+            work_terms += (unsigned)((Dmax >= 0 ? Dmax : -1) + 8) >> 3;
+            ++work_evals;
             double acc = 0.;
             // Left terms read y[L − n] (>= 0 because D <= L), right terms y[R + n]; beyond N the zero extension
             // contributes nothing.  When every active slot has 0 <= R and L < N (always, for candidates at positive
@@ -1029,6 +1049,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     P.lpf = (P.G + 1) / 2;
     P.ixmax = n / 2;
     P.fs = fs; P.fmin = fmin; P.fmax = fmax; P.threshold = threshold;
+    P.work = vbx_work_ptr(ctx);
     int T = 0;
     for (int p = 0; p < P.lpf; ++p) {
         const int gA = p, gB = P.G - 1 - p;
@@ -1037,18 +1058,27 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         if (t > T) T = t;
     }
     P.T = T;
-    P.xs_words = ((P.n16 + 48) * 5) / 4;  // 4 pad words per 16
+    // The sweep runs in fp64 (exact x·w products, one DFMA per lag product: vbx_pitch_lag64.cuh); VBX_PITCH_LAG=f32 selects
+    // the fp32-FMA sweep with fp64 folding (≈ 3e-8·r[0] in the lag function: enough for the top candidate, not for the
+    // weak entries of the list) for A/B runs.
+    const char* lv = getenv("VBX_PITCH_LAG");
+    const bool lag_f32 = lv && lv[0] == 'f' && lv[1] == '3' && !std::is_same<TIn, double>::value;
+    // frame buffer: fp32 with 4 pad words per 16, or f64 with 2 pad doubles per 16 (xs_words counts elements)
+    P.xs_words = lag_f32 ? ((P.n16 + 48) * 5) / 4 : ((P.n16 + 48) * 9) / 8;
     // frames per CTA: fill ~160 threads, bounded by shared memory (<= 56 KB so that 4 CTAs fit an SM)
     int fpc = 160 / P.lpf;
     if (fpc < 1) fpc = 1;
-    const size_t frame_bytes = (size_t)P.xs_words * sizeof(float);
+    const size_t frame_bytes = (size_t)P.xs_words * (lag_f32 ? sizeof(float) : sizeof(double));
     while (fpc > 1 && fpc * frame_bytes > 56 * 1024) --fpc;
     P.fpc = fpc;
     int threads = ((fpc * P.lpf + 31) / 32) * 32;
     if (threads < 64) threads = 64;
     const size_t smem = fpc * frame_bytes;
-    VBX_REQUIRE(ctx, smem <= ctx->smem_optin && threads <= 512, "frame_len %d does not fit the pitch kernel", n);
-    VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VBX_REQUIRE(ctx, smem <= ctx->smem_optin && threads <= (lag_f32 ? 512 : 256), "frame_len %d does not fit the pitch kernel", n);
+    if constexpr (!std::is_same<TIn, double>::value) {
+        if (lag_f32) VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (!lag_f32) VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag64_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // scratch per frame: y [N] f64 + worst-case candidate capacity (every other lag below N/2 a maximum)
     const int cap = P.ixmax / 2 + 1;
@@ -1080,8 +1110,11 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         VBX_CUDA(ctx, cudaMemsetAsync(P.counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
         const int64_t grid = (P.n_frames + fpc - 1) / fpc;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
-        pitch_lag_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
-        VBX_CHECK_LAUNCH(ctx, "pitch_lag_kernel");
+        if constexpr (!std::is_same<TIn, double>::value) {
+            if (lag_f32) pitch_lag_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+        }
+        if (!lag_f32) pitch_lag64_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+        VBX_CHECK_LAUNCH(ctx, lag_f32 ? "pitch_lag_kernel" : "pitch_lag64_kernel");
         if (refine_v0) {
             pitch_refine_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P);
         } else if (refine_v1) {
@@ -1097,7 +1130,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
             }();
             pitch_refine8q_kernel<<<ctx->sm_count * resident, 128, 0, ctx->stream>>>(P);
         }
-        VBX_CHECK_LAUNCH(ctx, "pitch_refine_kernel");
+        VBX_CHECK_LAUNCH(ctx, refine_v0 ? "pitch_refine_kernel" : (refine_v1 ? "pitch_refine8_kernel" : "pitch_refine8q_kernel"));
         pitch_finalize_kernel<<<(unsigned)((P.n_frames + 3) / 4), 128, 0, ctx->stream>>>(P, cand_out, max_cand, n_cand_out,
                                                                                         status_out, out_dtype == VBX_F64);
         VBX_CHECK_LAUNCH(ctx, "pitch_finalize_kernel");
@@ -1106,7 +1139,7 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
 }
 
 int pitch_check(vbx_ctx* ctx, const vbx_frames* fr, int max_cand, const void* cand_out, int out_dtype) {
-    int st = vbx_check_frames(ctx, fr);
+    int st = vbx_check_frames(ctx, fr, /*allow_f64=*/true);
     if (st != VBX_OK) return st;
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, max_cand >= 1, "max_candidates must be >= 1 (the unvoiced candidate always exists)");
@@ -1130,6 +1163,9 @@ int vbx_pitch(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double
     if (frames->dtype == VBX_I16)
         return launch_pitch<int16_t>(ctx, frames, sample_rate, threshold, min_hz, max_hz, max_candidates, cand_out, n_cand_out,
                                      status_out, out_dtype);
+    if (frames->dtype == VBX_F64)  // f64 samples (a frame the caller windowed in f64, as the reference's callers do)
+        return launch_pitch<double>(ctx, frames, sample_rate, threshold, min_hz, max_hz, max_candidates, cand_out, n_cand_out,
+                                    status_out, out_dtype);
     return launch_pitch<float>(ctx, frames, sample_rate, threshold, min_hz, max_hz, max_candidates, cand_out, n_cand_out,
                                status_out, out_dtype);
 }

@@ -43,6 +43,7 @@ struct RootsParams {
     int R;                 // resonance slots per frame in res_out
     int strict_im;         // 1: keep roots with im > 0 (lib.rs:95), 0: im >= 0 (to_resonance)
     int polish_steps;
+    unsigned long long* work;  // executed-work counters (vbx_profile_counters) or null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -136,10 +137,13 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     int M = P, it = 0;
     vcx<TR> z = cmk<TR>((TR)-2, (TR)-2);
     bool active = (P >= 3) && !lpc_failed;
+    unsigned work_steps = 0, work_rounds = 0;  // executed Horner steps / rounds of this lane (idle lanes run them too)
 #pragma unroll 1
     while (true) {
         const int Mmax = __reduce_max_sync(FULL, active ? M : 0);
         if (Mmax < 3) break;
+        work_steps += (unsigned)Mmax;
+        ++work_rounds;
         vcx<TR> a0 = c_s[Mmax * T + tid], a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
 #pragma unroll 4
         for (int j = Mmax - 1; j >= 0; --j) {
@@ -177,6 +181,12 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
                 z = cmk<TR>((TR)-2, (TR)-2);
                 active = (M >= 3);
             }
+        }
+    }
+    if (Q.work) {  // warp-uniform counts: one atomic pair per warp
+        if ((tid & 31) == 0) {
+            atomicAdd(Q.work + 0, 32ULL * work_steps);
+            atomicAdd(Q.work + 1, 32ULL * work_rounds);
         }
     }
     if (lpc_failed) {
@@ -315,10 +325,13 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     const vcx<TR> z_start = cmk<TR>((TR)0.3, (TR)0.9);
     vcx<TR> z = z_start;
     bool active = (P >= 3) && !lpc_failed;
+    unsigned work_steps = 0, work_rounds = 0;  // executed Horner steps / rounds of this lane (idle lanes run them too)
 #pragma unroll 1
     while (true) {
         const int Mmax = __reduce_max_sync(FULL, active ? M : 0);
         if (Mmax < 3) break;
+        work_steps += (unsigned)Mmax;
+        ++work_rounds;
         // Horner triple (P, P', P''/2) at z from the warp's largest degree: coefficients above a lane's own degree are 0
         vcx<TR> a0 = cmk<TR>(c_s[Mmax * T + tid], (TR)0), a1 = cmk<TR>((TR)0, (TR)0), a2 = cmk<TR>((TR)0, (TR)0);
 #pragma unroll 4
@@ -382,6 +395,12 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
                 z = z_start;
                 active = (M >= 3);
             }
+        }
+    }
+    if (Q.work) {  // warp-uniform counts: one atomic pair per warp
+        if ((tid & 31) == 0) {
+            atomicAdd(Q.work + 0, 32ULL * work_steps);
+            atomicAdd(Q.work + 1, 32ULL * work_rounds);
         }
     }
     if (lpc_failed) {

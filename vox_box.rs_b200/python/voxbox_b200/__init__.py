@@ -88,6 +88,7 @@ def _declare(L):
     sig("vbx_profile_end", C.c_int, _vp)
     sig("vbx_profile_count", C.c_int, _vp)
     sig("vbx_profile_entry", C.c_int, _vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64))
+    sig("vbx_profile_counters", C.c_int, _vp, C.POINTER(C.c_uint64), _i32)
     sig("vbx_window_table_host", C.c_int, C.c_int, _i32, C.POINTER(C.c_double))
     sig("vbx_autocorrelate", C.c_int, _vp, _frp, _i32, _vp, _i32)
     sig("vbx_autocorrelate_host", C.c_int, _vp, _frp, _i32, _vp, _i32)
@@ -126,6 +127,20 @@ def _declare(L):
     sig("vbx_max_amplitude", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _vp)
     sig("vbx_normalize", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _vp)
     sig("vbx_preemphasis", C.c_int, _vp, _vp, _i32, _i64, _i32, _i64, _d)
+    sig("vbx_find_formants_buffered", C.c_int, _vp, _frp, _d, _d, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
+    sig("vbx_synth_speech", C.c_int, _vp, _vp, _i32, _i64, _i64, _d, C.c_uint64, _i64)
+    sig("vbx_multi_create", C.c_int, _i32, C.POINTER(_i32), C.POINTER(_vp))
+    sig("vbx_multi_destroy", C.c_int, _vp)
+    sig("vbx_multi_device_count", _i32, _vp)
+    sig("vbx_multi_ctx", _vp, _vp, _i32)
+    sig("vbx_multi_last_error", C.c_char_p, _vp)
+    sig("vbx_multi_kernel_launches", _i64, _vp)
+    sig("vbx_multi_partition", None, _i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64))
+    sig("vbx_multi_lpc_host", C.c_int, _vp, _frp, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_multi_find_formants_host", C.c_int, _vp, _frp, C.c_double, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
+    sig("vbx_multi_pitch_host", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_multi_mfcc_host", C.c_int, _vp, _frp, _i32, _i32, _d, _d, _d, _vp, _i32)
+    sig("vbx_multi_h2d_bandwidth", C.c_int, _vp, _sz, _i32, _i32, C.POINTER(_d))
 
 
 def window_table(window, n):
@@ -238,6 +253,12 @@ class Context:
             self._check(self.lib.vbx_profile_entry(self.h, i, name, 128, C.byref(ms), C.byref(n)), "vbx_profile_entry")
             out[name.value.decode()] = (ms.value, n.value)
         return out
+
+    def profile_counters(self):
+        """Executed-work counters of the last profile_begin..profile_end window (vbx_profile_counters)."""
+        out = (C.c_uint64 * 8)()
+        self._check(self.lib.vbx_profile_counters(self.h, out, 8), "vbx_profile_counters")
+        return dict(roots_horner_steps=out[0], roots_rounds=out[1], refine_terms=out[2], refine_evals=out[3])
 
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)
@@ -627,3 +648,140 @@ def _pitch_viterbi(self, cand, n_cand, n_segments, voiced_unvoiced_cost=0.14, oc
 
 
 Context.pitch_viterbi = _pitch_viterbi
+
+
+def _find_formants_buffered(self, frames, fs, ratio, resampled_buf_len, p, estimates, dtype=F64):
+    """lib.rs:40-116 with the literal resampled_buf semantics over a device view."""
+    F = frames.n_frames
+    J = frames.frames_per_segment or F
+    segs = F // J if J else 0
+    est = np.ascontiguousarray(estimates, dtype=_NP[dtype])
+    k = est.shape[-2]
+    d_est = self.to_device(est.reshape(segs, k, 2))
+    tracks = self.empty((F, k, 2), _NP[dtype])
+    res = self.empty((F, MAX_RESONANCES, 2), _NP[dtype])
+    nres = self.empty((F,), np.int32)
+    st = self.empty((F,), np.uint8)
+    self._check(self.lib.vbx_find_formants_buffered(self.h, C.byref(frames), fs, ratio, resampled_buf_len, p, d_est.ptr, k,
+                                                    tracks.ptr, res.ptr, nres.ptr, st.ptr, dtype), "vbx_find_formants_buffered")
+    return dict(tracks=tracks.to_host(), estimates=d_est.to_host(), resonances=res.to_host(), n_res=nres.to_host(),
+                status=st.to_host())
+
+
+def _synth_speech(self, n_utts, n_samples, fs, seed=0x5EED, first_utt=0, dtype=F32, out=None):
+    """Synthetic speech-like corpus generated on the device → DeviceArray [n_utts][n_samples] (csrc/vbx_synth.cu)."""
+    d = out if out is not None else self.empty((n_utts, n_samples), _NP[dtype])
+    self._check(self.lib.vbx_synth_speech(self.h, d.ptr, dtype, n_utts, n_samples, float(fs), seed, first_utt), "vbx_synth_speech")
+    return d
+
+
+Context.find_formants_buffered = _find_formants_buffered
+Context.synth_speech = _synth_speech
+
+
+def multi_partition(n_units, n_parts, part):
+    lo, hi = _i64(0), _i64(0)
+    load_library().vbx_multi_partition(n_units, n_parts, part, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class _BorrowedContext(Context):
+    """A device context owned by a Multi handle (never destroyed from Python)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, _vp(handle)
+
+    def close(self):
+        self.h = None
+
+
+class Multi:
+    """vbx_multi: one worker thread + context per device; `_host` calls sharded by utterance, results gathered into the
+    caller's single host arrays (no torch / NCCL).  Fails loudly without the library / a GPU."""
+
+    def __init__(self, n_devices=0, devices=None):
+        self.lib = load_library()
+        h = _vp()
+        arr = (C.c_int32 * len(devices))(*devices) if devices else None
+        st = self.lib.vbx_multi_create(n_devices if not devices else len(devices), arr, C.byref(h))
+        if st != OK:
+            raise VoxBoxError(st, "vbx_multi_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.n = self.lib.vbx_multi_device_count(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vbx_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def ctx(self, i=0):
+        return _BorrowedContext(self.lib, self.lib.vbx_multi_ctx(self.h, i))
+
+    @property
+    def kernel_launches(self):
+        return self.lib.vbx_multi_kernel_launches(self.h)
+
+    def _check(self, st, what):
+        if st != OK:
+            raise VoxBoxError(st, f"{what}: {self.lib.vbx_multi_last_error(self.h).decode()} [{self.lib.vbx_status_str(st).decode()}]")
+
+    def h2d_bandwidth(self, bytes_per_device, reps=8, n_active=0):
+        out = (C.c_double * self.n)()
+        self._check(self.lib.vbx_multi_h2d_bandwidth(self.h, bytes_per_device, reps, n_active, out), "vbx_multi_h2d_bandwidth")
+        return list(out)
+
+    @staticmethod
+    def _view(audio, n_frames, frame_len, stride, window, frames_per_segment, segment_stride):
+        audio = np.ascontiguousarray(audio)
+        return audio, Context.frames(audio.ctypes.data, n_frames, frame_len, stride, window, I16 if audio.dtype == np.int16 else F32,
+                                     frames_per_segment, segment_stride)
+
+    def lpc_host(self, audio, n_frames, frame_len, stride, window, p, out_dtype=F64, frames_per_segment=0, segment_stride=0):
+        audio, fr = self._view(audio, n_frames, frame_len, stride, window, frames_per_segment, segment_stride)
+        r = np.zeros((n_frames, p + 1), dtype=_NP[out_dtype])
+        ac = np.zeros((n_frames, p + 1), dtype=_NP[out_dtype])
+        kc = np.zeros((n_frames, p), dtype=_NP[out_dtype])
+        self._check(self.lib.vbx_multi_lpc_host(self.h, C.byref(fr), p, r.ctypes.data, ac.ctypes.data, kc.ctypes.data, out_dtype),
+                    "vbx_multi_lpc_host")
+        return r, ac, kc
+
+    def find_formants_host(self, audio, n_frames, frame_len, stride, window, fs, p, method, estimates, dtype=F64,
+                           frames_per_segment=0, segment_stride=0):
+        audio, fr = self._view(audio, n_frames, frame_len, stride, window, frames_per_segment, segment_stride)
+        J = frames_per_segment or n_frames
+        segs = n_frames // J if J else 0
+        est = np.ascontiguousarray(estimates, dtype=_NP[dtype]).reshape(segs, -1, 2).copy()
+        k = est.shape[1]
+        tracks = np.zeros((n_frames, k, 2), dtype=_NP[dtype])
+        res = np.zeros((n_frames, MAX_RESONANCES, 2), dtype=_NP[dtype])
+        nres = np.zeros(n_frames, dtype=np.int32)
+        st = np.zeros(n_frames, dtype=np.uint8)
+        self._check(self.lib.vbx_multi_find_formants_host(self.h, C.byref(fr), fs, p, method, est.ctypes.data, k, tracks.ctypes.data,
+                                                          res.ctypes.data, nres.ctypes.data, st.ctypes.data, dtype),
+                    "vbx_multi_find_formants_host")
+        return dict(tracks=tracks, estimates=est, resonances=res, n_res=nres, status=st)
+
+    def pitch_host(self, audio, n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, max_cand=16, out_dtype=F64,
+                   frames_per_segment=0, segment_stride=0):
+        audio, fr = self._view(audio, n_frames, frame_len, stride, window, frames_per_segment, segment_stride)
+        cand = np.zeros((n_frames, max_cand, 2), dtype=_NP[out_dtype])
+        n = np.zeros(n_frames, dtype=np.int32)
+        st = np.zeros(n_frames, dtype=np.uint8)
+        self._check(self.lib.vbx_multi_pitch_host(self.h, C.byref(fr), fs, threshold, fmin, fmax, max_cand, cand.ctypes.data,
+                                                  n.ctypes.data, st.ctypes.data, out_dtype), "vbx_multi_pitch_host")
+        return dict(candidates=cand, n_cand=n, status=st)
+
+    def mfcc_host(self, audio, n_frames, frame_len, stride, window, num_coeffs, f_lo, f_hi, fs, n_keep=None, out_dtype=F64,
+                  frames_per_segment=0, segment_stride=0):
+        audio, fr = self._view(audio, n_frames, frame_len, stride, window, frames_per_segment, segment_stride)
+        n_keep = num_coeffs if n_keep is None else n_keep
+        out = np.zeros((n_frames, n_keep), dtype=_NP[out_dtype])
+        self._check(self.lib.vbx_multi_mfcc_host(self.h, C.byref(fr), num_coeffs, n_keep, f_lo, f_hi, fs, out.ctypes.data, out_dtype),
+                    "vbx_multi_mfcc_host")
+        return out
