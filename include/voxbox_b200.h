@@ -272,6 +272,10 @@ VBX_API int vbx_pitch(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
 VBX_API int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double threshold, double min_hz,
                            double max_hz, int32_t max_candidates, void* cand_out, int32_t* n_cand_out,
                            uint8_t* status_out, int32_t out_dtype);
+/* periodic.rs:403-408: the lag function the candidates are read from (`self_lag`: autocorrelate(N) of the windowed frame,
+ * normalize(), divided by the HanningLag window) for every frame of the view: lag_out [F][frame_len] f64 (device).  The reference
+ * zero-extends it to 2N (:411) before interpolating. */
+VBX_API int vbx_pitch_lag_function(vbx_ctx* ctx, const vbx_frames* frames, double* lag_out);
 /* periodic.rs:320-354 PitchExtractor::next: out[f] = candidates[f][0] (arg-max; the cost fields are unused). */
 VBX_API int vbx_pitch_extract(vbx_ctx* ctx, const void* cand, int32_t dtype, int64_t n_frames, int32_t max_candidates,
                               void* out);

@@ -111,6 +111,8 @@ def _declare(L):
         _dp, _i64, _dp, _dp, _i32p, _dp, _u8p, C.c_int)
     sig("vbo_batch_pitch", C.c_int, _fp, _i64, _i64, _i64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
         _dp, _i64, _i32p, _u8p, C.c_int)
+    sig("vbo_batch_pitch_variant", C.c_int, _fp, _i64, _i64, _i64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+        _dp, _i64, _i32p, _u8p, C.c_int)
     sig("vbo_batch_mfcc", C.c_int, _fp, _i64, _i64, _i64, C.c_int, _i64, C.c_double, C.c_double, C.c_double, _i64,
         _dp, C.c_int, C.c_int)
 
@@ -451,6 +453,18 @@ def batch_pitch(audio, n_frames, frame_len, stride, window, fs, threshold, fmin,
     st = np.zeros(n_frames, dtype=np.uint8)
     lib().vbo_batch_pitch(_f(a), n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, _d(cand), max_cand,
                           nc.ctypes.data_as(_i32p), st.ctypes.data_as(_u8p), n_threads)
+    return cand, nc, st
+
+
+def batch_pitch_variant(audio, n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, acf_variant, max_cand=16, n_threads=1):
+    """batch_pitch with a rounding-level variant of the autocorrelation fold (1: descending i, 2: fused multiply-add):
+    sensitivity experiments only (tools/pitch_sensitivity.py), never a parity target."""
+    a = _f32(audio)
+    cand = np.zeros((n_frames, max_cand, 2))
+    nc = np.zeros(n_frames, dtype=np.int32)
+    st = np.zeros(n_frames, dtype=np.uint8)
+    lib().vbo_batch_pitch_variant(_f(a), n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, acf_variant, _d(cand), max_cand,
+                                  nc.ctypes.data_as(_i32p), st.ctypes.data_as(_u8p), n_threads)
     return cand, nc, st
 
 

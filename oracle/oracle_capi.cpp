@@ -326,6 +326,29 @@ VBO_API int vbo_batch_pitch(const float* base, int64_t n_frames, int64_t n, int6
     return OK;
 }
 
+// the same loop with a rounding-level variant of the autocorrelation fold (tools/pitch_sensitivity.py)
+VBO_API int vbo_batch_pitch_variant(const float* base, int64_t n_frames, int64_t n, int64_t stride, int window_kind,
+                                    double fs, double threshold, double fmin, double fmax, int acf_variant,
+                                    double* cand_out, int64_t max_cand, int32_t* ncand_out, uint8_t* status_out, int n_threads) {
+    std::vector<double> win = make_window(window_kind, n);
+    int nt = threads_or_max(n_threads);
+    (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 16) if (nt > 1)
+    for (int64_t f = 0; f < n_frames; ++f) {
+        std::vector<double> xw(n);
+        for (int64_t i = 0; i < n; ++i) xw[i] = win.empty() ? double(base[f * stride + i]) : double(base[f * stride + i]) * win[i];
+        std::vector<Pitch> out;
+        int st = pitch(xw.data(), n, fs, threshold, fmin, fmax, out, nullptr, acf_variant);
+        if (status_out) status_out[f] = (uint8_t)st;
+        if (ncand_out) ncand_out[f] = (int32_t)out.size();
+        for (int64_t k = 0; k < max_cand; ++k) {
+            cand_out[(f * max_cand + k) * 2] = k < (int64_t)out.size() ? out[k].frequency : 0.;
+            cand_out[(f * max_cand + k) * 2 + 1] = k < (int64_t)out.size() ? out[k].strength : 0.;
+        }
+    }
+    return OK;
+}
+
 // MFCC over frames: out [F][n_keep] (first n_keep of num_coeffs DCT rows)
 VBO_API int vbo_batch_mfcc(const float* base, int64_t n_frames, int64_t n, int64_t stride, int window_kind,
                            int64_t num_coeffs, double f_lo, double f_hi, double fs, int64_t n_keep,

@@ -732,13 +732,32 @@ struct PitchDebug {
 // x: already-windowed frame (f64 values); returns candidates sorted by strength
 // descending, always containing {0, threshold}.  local_peak/global_peak are
 // ignored by the reference (periodic.rs:396) and therefore not parameters here.
+// Rounding-level variants of the reference's autocorrelation fold, for the SENSITIVITY experiments of
+// tools/pitch_sensitivity.py only (never a parity target): the same mathematical sums with a different rounding,
+// i.e. what any re-implementation that does not reproduce the reference's operation order bit for bit produces.
+//   1: terms added in descending i;   2: fused multiply-add (one rounding per term instead of two).
+inline void autocorrelate_rounding_variant(const double* x, size_t n, double* r, size_t n_lags, int variant) {
+    for (size_t lag = 0; lag < n_lags; ++lag) {
+        double acc = 0.0;
+        if (variant == 1) {
+            for (size_t i = n - lag; i-- > 1;) acc = acc + x[i] * x[i + lag];
+            acc = acc + x[0];
+        } else {
+            acc = x[0];
+            for (size_t i = 1; i + lag < n; ++i) acc = std::fma(x[i], x[i + lag], acc);
+        }
+        r[lag] = acc;
+    }
+}
+
 inline int pitch(const double* x, size_t n, double fs, double threshold, double fmin, double fmax,
-                 std::vector<Pitch>& out, PitchDebug* dbg = nullptr) {
+                 std::vector<Pitch>& out, PitchDebug* dbg = nullptr, int acf_variant = 0) {
     out.clear();
     if (n < 2) return ERR_BADARG;
     std::vector<double> window_lag = hanning_lag_window(n);           // :400
     std::vector<double> self_lag(n);
-    autocorrelate(x, n, self_lag.data(), n);                          // :403
+    if (acf_variant == 0) autocorrelate(x, n, self_lag.data(), n);    // :403
+    else autocorrelate_rounding_variant(x, n, self_lag.data(), n, acf_variant);
     normalize(self_lag.data(), n);                                    // :404
     for (size_t i = 0; i < n; ++i) self_lag[i] = self_lag[i] / window_lag[i];  // :406-408
     self_lag.resize(n * 2, 0.0);                                      // :411

@@ -1029,7 +1029,7 @@ constexpr int kMaxPitchFrameLen = 16384;
 
 template <typename TIn>
 int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold, double fmin, double fmax, int max_cand,
-                 void* cand_out, int32_t* n_cand_out, uint8_t* status_out, int out_dtype) {
+                 void* cand_out, int32_t* n_cand_out, uint8_t* status_out, int out_dtype, double* lag_out = nullptr) {
     const int n = fr->frame_len;
     const double* win = nullptr;
     const double* lagwin = nullptr;
@@ -1115,6 +1115,11 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         }
         if (!lag_f32) pitch_lag64_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
         VBX_CHECK_LAUNCH(ctx, lag_f32 ? "pitch_lag_kernel" : "pitch_lag64_kernel");
+        if (lag_out) {  // vbx_pitch_lag_function: hand the lag function out and stop here
+            VBX_CUDA(ctx, cudaMemcpyAsync(lag_out + (size_t)f0 * n, P.y, (size_t)P.n_frames * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                          ctx->stream));
+            continue;
+        }
         if (refine_v0) {
             pitch_refine_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P);
         } else if (refine_v1) {
@@ -1168,6 +1173,19 @@ int vbx_pitch(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double
                                     status_out, out_dtype);
     return launch_pitch<float>(ctx, frames, sample_rate, threshold, min_hz, max_hz, max_candidates, cand_out, n_cand_out,
                                status_out, out_dtype);
+}
+
+// periodic.rs:403-408: the lag function `self_lag` the candidates are read from — autocorrelate(N), normalize, divide by the
+// lag window — for every frame: lag_out [F][N] f64 (the reference then zero-extends it to 2N, :411).
+int vbx_pitch_lag_function(vbx_ctx* ctx, const vbx_frames* frames, double* lag_out) {
+    if (!ctx) return VBX_ERR_BADARG;
+    int st = pitch_check(ctx, frames, 1, lag_out, VBX_F64);
+    if (st != VBX_OK) return st;
+    if (frames->n_frames == 0) return VBX_OK;
+    cudaSetDevice(ctx->device);
+    if (frames->dtype == VBX_I16) return launch_pitch<int16_t>(ctx, frames, 1.0, 0.0, 0.0, 0.0, 1, nullptr, nullptr, nullptr, VBX_F64, lag_out);
+    if (frames->dtype == VBX_F64) return launch_pitch<double>(ctx, frames, 1.0, 0.0, 0.0, 0.0, 1, nullptr, nullptr, nullptr, VBX_F64, lag_out);
+    return launch_pitch<float>(ctx, frames, 1.0, 0.0, 0.0, 0.0, 1, nullptr, nullptr, nullptr, VBX_F64, lag_out);
 }
 
 int vbx_pitch_host(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate, double threshold, double min_hz, double max_hz,

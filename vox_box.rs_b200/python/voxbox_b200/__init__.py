@@ -113,6 +113,7 @@ def _declare(L):
     sig("vbx_find_formants_resampled", C.c_int, _vp, _frp, _d, _d, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32)
     sig("vbx_pitch", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
     sig("vbx_pitch_host", C.c_int, _vp, _frp, _d, _d, _d, _d, _i32, _vp, _vp, _vp, _i32)
+    sig("vbx_pitch_lag_function", C.c_int, _vp, _frp, _vp)
     sig("vbx_pitch_extract", C.c_int, _vp, _vp, _i32, _i64, _i32, _vp)
     sig("vbx_pitch_viterbi", C.c_int, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _d, _d, _d, _d, _vp, _vp)
     sig("vbx_interpolate_sinc", C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp)
@@ -519,7 +520,15 @@ def _improve_extremum(self, y, offset, nx, ixmid, interp=INTERP_SINC, depth=1200
     return xm.to_host(), ym.to_host()
 
 
+def _pitch_lag_function(self, frames):
+    """periodic.rs:403-408 self_lag for every frame → device array [F][N] f64."""
+    out = self.empty((frames.n_frames, frames.frame_len), np.float64)
+    self._check(self.lib.vbx_pitch_lag_function(self.h, C.byref(frames), out.ptr), "vbx_pitch_lag_function")
+    return out
+
+
 Context.pitch = _pitch
+Context.pitch_lag_function = _pitch_lag_function
 Context.pitch_host = _pitch_host
 Context.pitch_extract = _pitch_extract
 Context.interpolate_sinc = _interpolate_sinc
