@@ -629,10 +629,12 @@ class Workload:
         return {
             "lpc": {"lpc_fused16_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), "r1_lpc16_final_full.txt", alg),
                     "lpc_fused_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_final_full.txt", alg),
-                    "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), None, alg)},
+                    "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), None, alg),
+                    "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), None, alg)},
             "formants": {
                 "lpc_fused_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r1_lpc_final_full.txt", alg),
-                "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), None, alg),
+                "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r2_lpca_v1_full.txt", alg),
+                "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), None, alg),
                 "lpc_fused16_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r1_lpc16_final_full.txt", alg),
                 "lpc_roots_pair_kernel": ("fp32", roots_flop, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt", cnt),
                 "lpc_roots_rt_kernel": ("fp32", roots_flop, 8 * (p + 1) + 8 * p + 5, None, cnt),

@@ -269,3 +269,185 @@ def test_multi_partition_rule():
     assert lo_hi[0][0] == 0 and lo_hi[-1][1] == 4500
     assert all(a[1] == b[0] for a, b in zip(lo_hi, lo_hi[1:]))
     assert max(h - l for l, h in lo_hi) - min(h - l for l, h in lo_hi) <= 1
+
+
+# ------------------------------------------------------------------------------------- frame-chunk pipelining of find_formants
+@pytest.mark.parametrize("method,window", [(vb.LPC_AUTOCORR, vb.WINDOW_HANN_SYMMETRIC), (vb.LPC_BURG, vb.WINDOW_HANN_PERIODIC)])
+@pytest.mark.parametrize("segmented", [True, False])
+def test_find_formants_frame_chunks_identical(monkeypatch, method, window, segmented):
+    """vbx_find_formants processes the frames of every utterance in chunks (LPC + roots of chunk c + 1 on the main stream while
+    the tracker steps through chunk c on the side stream): any chunk count gives bit-identical tracks, state, resonances,
+    counts and status."""
+    c = ctx()
+    fs, N, hop, U = 16000, 400, 160, 5
+    ns = fs * 2
+    d = c.synth_speech(U, ns, fs, first_utt=900)
+    J = c.n_frames_of(ns, N, hop)
+    if segmented:
+        fr = c.frames(d.ptr, U * J, N, hop, window, frames_per_segment=J, segment_stride=ns)
+        est = np.tile(MALE, (U, 1, 1))
+    else:
+        fr = c.frames(d.ptr, c.n_frames_of(U * ns, N, hop), N, hop, window)
+        est = MALE[None]
+    monkeypatch.setenv("VBX_FORMANT_CHUNKS", "1")
+    ref = c.find_formants(fr, float(fs), 12, method, est)
+    ref_tracks_only = c.find_formants(fr, float(fs), 12, method, est, want_resonances=False)
+    for k in ("3", "5", "8", "1000"):
+        monkeypatch.setenv("VBX_FORMANT_CHUNKS", k)
+        c.profile_begin()
+        out = c.find_formants(fr, float(fs), 12, method, est)
+        names = c.profile_end()
+        assert names["tracker_idx_kernel"][1] == min(int(k), fr.frames_per_segment or fr.n_frames)
+        for key in ("tracks", "estimates", "resonances", "n_res", "status"):
+            assert np.array_equal(out[key], ref[key]), (k, key)
+        out2 = c.find_formants(fr, float(fs), 12, method, est, want_resonances=False)
+        assert np.array_equal(out2["tracks"], ref_tracks_only["tracks"]) and np.array_equal(out2["estimates"], ref_tracks_only["estimates"])
+    assert np.array_equal(ref_tracks_only["tracks"], ref["tracks"])
+
+
+# ------------------------------------------------------------------------------------- the aligned-down LPC kernel (vbx_lpca.cuh)
+@pytest.mark.parametrize("N,hop,p,window", [(1102, 441, 12, vb.WINDOW_HANN_SYMMETRIC), (1102, 441, 12, vb.WINDOW_NONE), (333, 100, 12, vb.WINDOW_HANN_SYMMETRIC),
+                                             (257, 100, 8, vb.WINDOW_HANN_PERIODIC), (64, 64, 4, vb.WINDOW_NONE), (17, 5, 12, vb.WINDOW_NONE),
+                                             (50, 50, 1, vb.WINDOW_HANN_SYMMETRIC), (2047, 1, 12, vb.WINDOW_HANN_SYMMETRIC)])
+@pytest.mark.parametrize("plan", ["32:8", "16:8", "32:4", "8:4"])
+def test_lpc_aligned_kernel_shapes(oracle, monkeypatch, N, hop, p, window, plan):
+    c = ctx()
+    monkeypatch.setenv("VBX_LPCA_PLAN", plan)
+    monkeypatch.setenv("VBX_LPC16", "0")
+    audio = synth.utterance(77, 16000, seconds=1.0)
+    F = min(c.n_frames_of(audio.size, N, hop), 300)
+    d = c.to_device(audio)
+    c.profile_begin()
+    r, ac, kc = c.lpc(c.frames(d.ptr, F, N, hop, window), p)
+    names = c.profile_end()
+    if plan.startswith("32:"):  # smaller CTAs may not reach a whole warp once K shrinks for a short frame: general kernel then
+        assert "lpc_fuseda_kernel" in names, names
+    rr, ra, rk = oracle.batch_lpc(audio, F, N, hop, window, p, want_kc=True)
+    assert np.max(normwise(r.to_host(), rr)) < 1e-12
+    assert np.max(normwise(ac.to_host(), ra)) < 1e-8
+    assert np.max(normwise(kc.to_host(), rk)) < 1e-8
+
+
+def test_lpc_aligned_kernel_unaligned_base_segments_pcm_and_nonfinite(oracle):
+    c = ctx()
+    fs, N, hop, p = 44100, 1102, 441, 12
+    audio = synth.corpus(3, fs, seconds=1.0, first=60)  # 3 utterances x 44100 samples
+    ns = audio.shape[1]
+    J = c.n_frames_of(ns, N, hop)
+    # (1) every base alignment, segmented view
+    flat = np.concatenate([np.zeros(8, np.float32), audio.reshape(-1), np.zeros(8, np.float32)])
+    d = c.to_device(flat)
+    for off in range(8):
+        x = flat[off:off + 3 * ns].reshape(3, ns)
+        c.profile_begin()
+        r, ac, _ = c.lpc(c.frames(d.ptr + 4 * off, 3 * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=ns), p)
+        assert "lpc_fuseda_kernel" in c.profile_end()
+        rr = np.concatenate([oracle.batch_lpc(np.ascontiguousarray(x[u]), J, N, hop, oracle.WIN_HANN_SYMMETRIC, p)[0] for u in range(3)])
+        assert np.max(normwise(r.to_host(), rr)) < 1e-12, off
+    # (2) int16 PCM, odd sample offsets
+    pcm = np.clip(np.round(audio[0].astype(np.float64) * 32767), -32768, 32767).astype(np.int16)
+    dp = c.to_device(np.concatenate([np.zeros(8, np.int16), pcm]))
+    for off in (0, 1, 3, 5, 7):
+        fr = c.frames(dp.ptr + 2 * (8 - off), c.n_frames_of(ns - 8, N, hop), N, hop, vb.WINDOW_HANN_SYMMETRIC, dtype=vb.I16)
+        r, ac, _ = c.lpc(fr, p)
+        x = np.concatenate([np.zeros(off, np.int16), pcm])[: ns].astype(np.float32) / np.float32(1.0)
+        xs = (np.concatenate([np.zeros(off), pcm.astype(np.float64)]) / 32767.0)
+        w = oracle.hanning_window(N)
+        rr = np.stack([oracle.autocorrelate(xs[f * hop:f * hop + N] * w, p + 1) for f in range(fr.n_frames)])
+        assert np.max(normwise(r.to_host(), rr)) < 1e-9, off  # sample/32767·w vs sample·(w/32767): an ulp of f64
+    # (3) non-finite samples: a NaN / Inf poisons exactly the frames that contain it (the zero-weight neighbours do not)
+    bad = audio[0].copy()
+    bad[5000] = np.nan
+    bad[20000] = np.inf
+    bad[20001] = -np.inf
+    db = c.to_device(bad)
+    r, ac, _ = c.lpc(c.frames(db.ptr, J, N, hop, vb.WINDOW_HANN_SYMMETRIC), p)
+    rr, ra = oracle.batch_lpc(bad, J, N, hop, oracle.WIN_HANN_SYMMETRIC, p)
+    rg = r.to_host()
+    assert np.array_equal(np.isnan(rg), np.isnan(rr))
+    ok = ~np.isnan(rr).any(axis=1)
+    assert ok.sum() > J // 2 and np.max(normwise(rg[ok], rr[ok])) < 1e-12
+
+
+def test_find_formants_c3_uses_aligned_kernel(oracle):
+    c = ctx()
+    fs, N, hop = 44100, 1102, 441
+    d = c.synth_speech(4, fs * 2, fs, first_utt=1234)
+    audio = d.to_host()
+    J = c.n_frames_of(fs * 2, N, hop)
+    fr = c.frames(d.ptr, 4 * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=fs * 2)
+    c.profile_begin()
+    out = c.find_formants(fr, float(fs), 12, vb.LPC_AUTOCORR, np.tile(MALE, (4, 1, 1)))
+    names = c.profile_end()
+    assert "lpc_fuseda_kernel" in names
+    for u in range(4):
+        o = oracle.batch_formants(audio[u], J, N, hop, oracle.WIN_HANN_SYMMETRIC, 1, float(fs), 12, np.array([0, J]), MALE)
+        sl = slice(u * J, (u + 1) * J)
+        assert np.array_equal(out["n_res"][sl], o["n_res"])
+        assert np.max(np.abs(out["tracks"][sl] - o["tracks"])) < 0.5
+
+
+# ------------------------------------------------------------------------------------- the persistent TMA-fed LPC kernel
+@pytest.mark.parametrize("N,hop,p,fs", [(1102, 441, 12, 44100), (400, 100, 12, 16000), (333, 333, 5, 16000), (1000, 30, 12, 16000)])
+def test_lpc_persistent_kernel(oracle, monkeypatch, N, hop, p, fs):
+    """Batches with at least two tiles of 32 frames per SM take lpc_fusedp_kernel (warp-specialised, TMA + mbarrier ring);
+    same arithmetic as the one-shot aligned kernel: bit-identical to it, and within rounding of the oracle.  Covers ragged
+    last tiles of a segment, every base alignment, a non-finite sample, and fewer parts."""
+    c = ctx()
+    monkeypatch.setenv("VBX_LPC16", "0")
+    U = 14
+    ns = fs * 3 + 7  # odd utterance length: segment starts walk through the alignments
+    d = c.synth_speech(U, ns, fs, first_utt=4242)
+    audio = d.to_host()
+    J = c.n_frames_of(ns, N, hop)
+    tiles = U * ((J + 31) // 32)
+    sm = c.sm_count
+    fr = c.frames(d.ptr, U * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=ns)
+    c.profile_begin()
+    r, ac, kc = c.lpc(fr, p)
+    names = c.profile_end()
+    if tiles >= 2 * sm:
+        assert "lpc_fusedp_kernel" in names, (names, tiles)
+    rg, ag, kg = r.to_host(), ac.to_host(), kc.to_host()
+    monkeypatch.setenv("VBX_LPCP", "0")
+    c.profile_begin()
+    r2, ac2, kc2 = c.lpc(fr, p)
+    assert "lpc_fuseda_kernel" in c.profile_end()
+    monkeypatch.delenv("VBX_LPCP")
+    assert np.array_equal(rg, r2.to_host()) and np.array_equal(ag, ac2.to_host()) and np.array_equal(kg, kc2.to_host())
+    for u in (0, 5, U - 1):
+        rr, ra = oracle.batch_lpc(audio[u], J, N, hop, oracle.WIN_HANN_SYMMETRIC, p)
+        assert np.max(normwise(rg[u * J:(u + 1) * J], rr)) < 1e-12
+        assert np.max(normwise(ag[u * J:(u + 1) * J], ra)) < 1e-8
+    # fewer parts, fp32 outputs, r only
+    monkeypatch.setenv("VBX_LPCP_K", "4")
+    r4, a4, _ = c.lpc(fr, p, out_dtype=vb.F32, want_kc=False)
+    monkeypatch.delenv("VBX_LPCP_K")
+    assert np.max(normwise(r4.to_host(), rg)) < 1e-6 and np.max(normwise(a4.to_host(), ag)) < 1e-5
+
+
+def test_lpc_persistent_kernel_nonfinite_and_alignment(oracle, monkeypatch):
+    c = ctx()
+    fs, N, hop, p = 44100, 1102, 441, 12
+    U, ns = 32, 44100 * 3  # 32 x 10 tiles >= 2 per SM
+    base = c.synth_speech(U, ns, fs, first_utt=99).to_host()
+    for off in range(4):
+        flat = np.concatenate([np.zeros(off, np.float32), base.reshape(-1), np.zeros(16, np.float32)])
+        x = flat[off:off + U * ns].reshape(U, ns).copy()
+        if off == 1:
+            flat[off + 5000] = np.nan            # inside frames
+            flat[off + 2 * ns + 441 * 7 - 1] = np.inf  # one sample before frame 7 of utterance 2: a zero-weight neighbour for a = 1..3
+            x = flat[off:off + U * ns].reshape(U, ns).copy()
+        d = c.to_device(flat)
+        J = c.n_frames_of(ns, N, hop)
+        fr = c.frames(d.ptr + 4 * off, U * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=ns)
+        c.profile_begin()
+        r, ac, _ = c.lpc(fr, p)
+        assert "lpc_fusedp_kernel" in c.profile_end()
+        rg = r.to_host()
+        for u in (0, 2, U - 1):
+            rr, _ = oracle.batch_lpc(np.ascontiguousarray(x[u]), J, N, hop, oracle.WIN_HANN_SYMMETRIC, p)
+            sl = rg[u * J:(u + 1) * J]
+            assert np.array_equal(np.isnan(sl), np.isnan(rr)), (off, u)
+            ok = np.isfinite(rr).all(axis=1)
+            assert np.max(normwise(sl[ok], rr[ok])) < 1e-12, (off, u)

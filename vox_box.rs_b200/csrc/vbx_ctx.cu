@@ -31,8 +31,24 @@ void vbx_prof_mark(vbx_ctx* ctx, const char* name) {
     ctx->prof_used++;
 }
 
+int vbx_prof_range_begin(vbx_ctx* ctx, const char* name, cudaStream_t stream) {
+    if (!ctx->prof_on || ctx->prof_ranges.size() >= 65536) return -1;
+    vbx_ctx::ProfRange r;
+    r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(r.e0); return -1; }
+    cudaEventRecord(r.e0, stream);
+    ctx->prof_ranges.push_back(r);
+    return (int)ctx->prof_ranges.size() - 1;
+}
+void vbx_prof_range_end(vbx_ctx* ctx, int slot, cudaStream_t stream) {
+    if (slot >= 0 && slot < (int)ctx->prof_ranges.size()) cudaEventRecord(ctx->prof_ranges[slot].e1, stream);
+}
+
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->arena_bytes) return VBX_OK;
+    // a tracker of an earlier vbx_find_formants call may still read the block from the side stream
+    if (ctx->s_side) cudaStreamSynchronize(ctx->s_side);
     // grow-only; the stream is drained first so no in-flight kernel still uses the old block
     VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->arena) cudaFree(ctx->arena);
@@ -256,6 +272,15 @@ int vbx_ctx_create(int device, vbx_ctx** out) {
             delete ctx;
             return VBX_ERR_CUDA;
         }
+    if (cudaMalloc(&ctx->tile_counter, 256) != cudaSuccess) { delete ctx; return VBX_ERR_CUDA; }
+    {
+        // the tracker's CTAs should be dispatched ahead of the queued LPC / roots grids: highest priority
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->s_side, cudaStreamNonBlocking, hi) != cudaSuccess) { delete ctx; return VBX_ERR_CUDA; }
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return VBX_ERR_CUDA; }
+    }
     *out = ctx;
     return VBX_OK;
 }
@@ -268,10 +293,14 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
     vbx_mfcc_cache_free(ctx);
     for (auto e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->work_counters) cudaFree(ctx->work_counters);
+    if (ctx->tile_counter) cudaFree(ctx->tile_counter);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pipe) cudaFree(ctx->pipe);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev_pipe[i]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev_side[i]);
+    for (auto& r : ctx->prof_ranges) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
     cudaStreamDestroy(ctx->s_h2d);
     cudaStreamDestroy(ctx->s_d2h);
     cudaEventDestroy(ctx->ev_start);
@@ -284,6 +313,7 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
 int vbx_sync(vbx_ctx* ctx) {
     if (!ctx) return VBX_ERR_BADARG;
     VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->s_side) VBX_CUDA(ctx, cudaStreamSynchronize(ctx->s_side));
     return VBX_OK;
 }
 
@@ -365,6 +395,8 @@ int vbx_profile_begin(vbx_ctx* ctx) {
     ctx->prof_used = 0;
     ctx->prof_names.clear();
     ctx->prof_totals.clear();
+    for (auto& r : ctx->prof_ranges) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    ctx->prof_ranges.clear();
     cudaSetDevice(ctx->device);
     if (!ctx->work_counters) {
         if (cudaMalloc(&ctx->work_counters, VBX_N_WORK_COUNTERS * sizeof(unsigned long long)) != cudaSuccess) {
@@ -382,6 +414,14 @@ int vbx_profile_end(vbx_ctx* ctx) {
     if (!ctx) return VBX_ERR_BADARG;
     ctx->prof_on = false;
     VBX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->s_side) VBX_CUDA(ctx, cudaStreamSynchronize(ctx->s_side));
+    for (auto& r : ctx->prof_ranges) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto& t = ctx->prof_totals[r.name];
+        t.first += ms;
+        t.second += 1;
+    }
     for (size_t i = 1; i < ctx->prof_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->prof_events[i - 1], ctx->prof_events[i]) != cudaSuccess) { cudaGetLastError(); continue; }

@@ -14,6 +14,7 @@
 //                         deflation in fp32 (or fp64), fp64 Newton polish on the original polynomial,
 //                         resonances computed and rank-sorted in fp64.
 //   tracker_kernel        one thread per utterance, sequential over its frames (McCandless step).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -437,6 +438,7 @@ struct TrackParams {
     int64_t n_segments, seg_frames;
     int R, n_res_eff;       // stored slots per frame; number of resonances the step sees (zero padded up to it)
     int n_est, res_f64, out_f64;
+    int64_t j_begin, j_count;  // the frames [j_begin, j_begin + j_count) of every segment are stepped through (state in est_inout)
 };
 
 // One warp per utterance (segment).  Lane j holds resonance j of the current frame (32 lanes = the 32
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(128) tracker_kernel(const TrackParams T) {
         xf = ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2);
         xb = ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + lane) * 2 + 1);
     }
-    const int64_t f0 = u * T.seg_frames;
+    const int64_t f0 = u * T.seg_frames + T.j_begin;
     auto load_res = [&](int64_t f, double& rf, double& rb, int& st) {
         rf = 0.0; rb = 0.0;
         if (lane < T.R && lane < T.n_res_eff) {
@@ -484,11 +486,11 @@ __global__ void __launch_bounds__(128) tracker_kernel(const TrackParams T) {
     double nrf, nrb;
     int nst;
     load_res(f0, nrf, nrb, nst);
-    for (int64_t j = 0; j < T.seg_frames; ++j) {
+    for (int64_t j = 0; j < T.j_count; ++j) {
         const int64_t f = f0 + j;
         const double rf = nrf, rb = nrb;
         const int st = nst;
-        if (j + 1 < T.seg_frames) load_res(f + 1, nrf, nrb, nst);  // prefetch
+        if (j + 1 < T.j_count) load_res(f + 1, nrf, nrb, nst);  // prefetch
         if (st == VBX_OK) {
             double sf[NS], sb[NS];
             bool some[NS];
@@ -625,13 +627,14 @@ __global__ void __launch_bounds__(128) tracker_kernel(const TrackParams T) {
 // chunks, [chunk][thread] layout), nres/status are prefetched one frame ahead, and a warp advances 32
 // utterances per instruction.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrkThreads = 64;
+constexpr int kTrkThreads = 64;        // stand-alone launches: many small CTAs, one or two warps per SM
+constexpr int kTrkThreadsPacked = 512; // vbx_find_formants' side stream: few big CTAs (see estimate_formants_impl)
 
 template <bool RES_F64>
-__global__ void __launch_bounds__(kTrkThreads) tracker_idx_kernel(const TrackParams T, const int chunks_per_row) {
+__global__ void __launch_bounds__(kTrkThreadsPacked) tracker_idx_kernel(const TrackParams T, const int chunks_per_row) {
     extern __shared__ __align__(16) unsigned char trk_smem[];
     constexpr int NS = VBX_MAX_FORMANT_SLOTS;
-    constexpr int TT = kTrkThreads;
+    const int TT = blockDim.x;
     constexpr int NONE = -1;
     const int tid = threadIdx.x;
     const int64_t u = (int64_t)blockIdx.x * TT + tid;
@@ -641,7 +644,7 @@ __global__ void __launch_bounds__(kTrkThreads) tracker_idx_kernel(const TrackPar
     const int n_stored = R < T.n_res_eff ? R : T.n_res_eff;
     const size_t row_bytes = (size_t)R * (RES_F64 ? 16 : 8);
     uint4* buf = reinterpret_cast<uint4*>(trk_smem);  // [2][chunks_per_row][TT] 16-byte chunks
-    const char* res_base = reinterpret_cast<const char*>(T.res) + (size_t)u * T.seg_frames * row_bytes;
+    const char* res_base = reinterpret_cast<const char*>(T.res) + ((size_t)u * T.seg_frames + T.j_begin) * row_bytes;
     auto issue = [&](int64_t j, int b) {
         const char* src = res_base + (size_t)j * row_bytes;
         for (int c = 0; c < chunks_per_row; ++c) {
@@ -665,18 +668,18 @@ __global__ void __launch_bounds__(kTrkThreads) tracker_idx_kernel(const TrackPar
         ef[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2) : 0.0;
         eb[k] = (k < n_est) ? ld_pair(T.est_inout, T.out_f64, ((size_t)u * n_est + k) * 2 + 1) : 0.0;
     }
-    const int64_t f0 = u * T.seg_frames;
+    const int64_t f0 = u * T.seg_frames + T.j_begin;
     int st_next = 0, nres_next = 0;
-    if (T.seg_frames > 0) {
+    if (T.j_count > 0) {
         issue(0, 0);
         st_next = T.status ? (int)T.status[f0] : 0;
         nres_next = T.nres[f0];
     }
-    for (int64_t j = 0; j < T.seg_frames; ++j) {
+    for (int64_t j = 0; j < T.j_count; ++j) {
         const int64_t f = f0 + j;
         const int b = (int)(j & 1);
         const int st = st_next, nres_f = nres_next;
-        if (j + 1 < T.seg_frames) {
+        if (j + 1 < T.j_count) {
             issue(j + 1, b ^ 1);
             st_next = T.status ? (int)T.status[f + 1] : 0;
             nres_next = T.nres[f + 1];
@@ -874,10 +877,10 @@ int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs
     return launch_burg<float>(ctx, frames, p, coeffs_out, status_out, out_dtype);
 }
 
-int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
-                          int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im, const uint8_t* status_in,
-                          void* res_out, int32_t res_slots, int32_t* nres_out, void* roots_out, uint8_t* status_out,
-                          int32_t out_dtype, int32_t precision) {
+static int lpc_to_resonances_impl(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
+                                  int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im, const uint8_t* status_in,
+                                  void* res_out, int32_t res_slots, int32_t* nres_out, void* roots_out, uint8_t* status_out,
+                                  int32_t out_dtype, int32_t precision, int64_t in_J, int64_t out_J, int64_t out_j0) {
     if (!ctx) return VBX_ERR_BADARG;
     VBX_REQUIRE(ctx, lpc_dtype == VBX_F32 || lpc_dtype == VBX_F64, "lpc_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
@@ -894,7 +897,16 @@ int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int6
     Q.lpc_has_one = lpc_has_leading_one ? 1 : 0; Q.lpc_f64 = (lpc_dtype == VBX_F64); Q.out_f64 = (out_dtype == VBX_F64);
     Q.R = res_slots; Q.strict_im = strict_im ? 1 : 0; Q.polish_steps = 2;
     Q.work = vbx_work_ptr(ctx);
+    Q.in_J = in_J; Q.out_J = out_J; Q.out_j0 = out_j0;
     return launch_lpc_roots(ctx, Q, p, precision < 0 ? root_precision_default() : precision);
+}
+
+int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
+                          int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im, const uint8_t* status_in,
+                          void* res_out, int32_t res_slots, int32_t* nres_out, void* roots_out, uint8_t* status_out,
+                          int32_t out_dtype, int32_t precision) {
+    return lpc_to_resonances_impl(ctx, lpc, lpc_dtype, n_frames, lpc_stride, p, lpc_has_leading_one, sample_rate, strict_im, status_in,
+                                  res_out, res_slots, nres_out, roots_out, status_out, out_dtype, precision, 0, 0, 0);
 }
 
 int vbx_find_roots(vbx_ctx* ctx, const void* coeffs, int32_t dtype, int64_t n_polys, int32_t len, void* roots_out,
@@ -978,8 +990,11 @@ int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dtype, int6
 // nres (optional, internal): per-frame count of real resonances when every stored entry behind it is known to be (0, 0)
 static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
                                   int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
-                                  int32_t n_estimates, void* tracks_out, int32_t dtype, const int32_t* nres) {
+                                  int32_t n_estimates, void* tracks_out, int32_t dtype, const int32_t* nres,
+                                  int64_t j_begin = 0, int64_t j_count = -1, cudaStream_t stream = nullptr) {
     if (!ctx) return VBX_ERR_BADARG;
+    if (!stream) stream = ctx->stream;
+    if (j_count < 0) j_count = frames_per_segment - j_begin;
     VBX_REQUIRE(ctx, res_dtype == VBX_F32 || res_dtype == VBX_F64, "res_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, dtype == VBX_F32 || dtype == VBX_F64, "dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, res_slots >= 1, "res_slots must be >= 1");
@@ -993,6 +1008,8 @@ static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t 
     T.res = resonances; T.nres = nres; T.status = status_in; T.est_inout = est_inout; T.tracks_out = tracks_out;
     T.n_segments = n_segments; T.seg_frames = frames_per_segment; T.R = res_slots; T.n_res_eff = n_resonances;
     T.n_est = n_estimates; T.res_f64 = (res_dtype == VBX_F64); T.out_f64 = (dtype == VBX_F64);
+    T.j_begin = j_begin; T.j_count = j_count;
+    const bool side = (stream != ctx->stream);  // side-stream launches are timed as explicit event pairs
     // fused path (per-frame counts known, rows sorted and zero padded): the index-based thread-per-utterance kernel,
     // when the rows can be staged with 16-byte cp.async chunks.  Arbitrary caller resonances (vbx_estimate_formants),
     // odd fp32 row lengths, or VBX_TRACKER=warp (A/B runs): the value-based warp-per-utterance kernel.
@@ -1001,24 +1018,56 @@ static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t 
     const char* tv = getenv("VBX_TRACKER");
     const bool aligned = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(resonances) & 15) == 0);
     const int chunks = (int)(row_bytes / 16);
-    const size_t smem = (size_t)2 * chunks * kTrkThreads * 16;
+    // On vbx_find_formants' side stream the tracker runs next to the LPC / roots grids of the following frame chunk.  With its
+    // small CTAs spread over every SM, each of its warps competes with 8-16 busy warps for issue slots and the (purely
+    // latency-bound) step chain runs 4-5x slower — slower than the main stream's chunk, so the tracker became the critical path
+    // (measured: 1.2 ms per chunk against 0.27 alone).  The persistent LPC kernel therefore leaves a few SMs free
+    // (ctx->reserve_sms): the block scheduler puts the tracker's CTAs there, 8 per SM, where they keep the issue slots largely
+    // to themselves (0.66 ms per chunk, hidden).  VBX_TRACKER_THREADS packs it into bigger CTAs (A/B runs: no better).
+    int trk_threads = kTrkThreads;
+    if (const char* e = getenv("VBX_TRACKER_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= kTrkThreadsPacked && v % 32 == 0) trk_threads = v;
+    }
+    while (trk_threads > 32 && (size_t)2 * chunks * trk_threads * 16 > ctx->smem_optin) trk_threads >>= 1;
+    const size_t smem = (size_t)2 * chunks * trk_threads * 16;
     if (nres && aligned && smem <= ctx->smem_optin && !(tv && tv[0] == 'w')) {
-        const int64_t grid = (n_segments + kTrkThreads - 1) / kTrkThreads;
+        const int64_t grid = (n_segments + trk_threads - 1) / trk_threads;
         VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
         if (res_dtype == VBX_F64) {
             VBX_CUDA(ctx, cudaFuncSetAttribute(tracker_idx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tracker_idx_kernel<true><<<(unsigned)grid, kTrkThreads, smem, ctx->stream>>>(T, chunks);
+            const int slot = side ? vbx_prof_range_begin(ctx, "tracker_idx_kernel", stream) : -1;
+            tracker_idx_kernel<true><<<(unsigned)grid, trk_threads, smem, stream>>>(T, chunks);
+            if (side) vbx_prof_range_end(ctx, slot, stream);
         } else {
             VBX_CUDA(ctx, cudaFuncSetAttribute(tracker_idx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tracker_idx_kernel<false><<<(unsigned)grid, kTrkThreads, smem, ctx->stream>>>(T, chunks);
+            const int slot = side ? vbx_prof_range_begin(ctx, "tracker_idx_kernel", stream) : -1;
+            tracker_idx_kernel<false><<<(unsigned)grid, trk_threads, smem, stream>>>(T, chunks);
+            if (side) vbx_prof_range_end(ctx, slot, stream);
         }
-        VBX_CHECK_LAUNCH(ctx, "tracker_idx_kernel");
+        if (side) {
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "launch of tracker_idx_kernel failed: %s", cudaGetErrorString(e));
+            ctx->launches++;
+        } else {
+            VBX_CHECK_LAUNCH(ctx, "tracker_idx_kernel");
+        }
         return VBX_OK;
     }
     const int64_t grid = (n_segments + 3) / 4;  // one warp per segment
     VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many segments for one launch");
-    tracker_kernel<<<(unsigned)grid, 128, 0, ctx->stream>>>(T);
-    VBX_CHECK_LAUNCH(ctx, "tracker_kernel");
+    {
+        const int slot = side ? vbx_prof_range_begin(ctx, "tracker_kernel", stream) : -1;
+        tracker_kernel<<<(unsigned)grid, 128, 0, stream>>>(T);
+        if (side) vbx_prof_range_end(ctx, slot, stream);
+    }
+    if (side) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "launch of tracker_kernel failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else {
+        VBX_CHECK_LAUNCH(ctx, "tracker_kernel");
+    }
     return VBX_OK;
 }
 
@@ -1047,10 +1096,44 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     if (F == 0) return VBX_OK;
     cudaSetDevice(ctx->device);
     const int p = n_coeffs;
-    // scratch: lpc [F][p+1] f64 | status [F] | resonances [F][p] pairs (if the caller does not want them)
+    const int64_t J = vbx_frames_per_segment(frames), segs = F / J;
+    const bool track = (n_formants > 0 && est_inout);
+    // Frame chunks.  The tracker is sequential over the frames of an utterance (998 steps of ~2 µs however many utterances
+    // there are), so run after everything else it would add its whole latency to the call.  Instead the frames of EVERY
+    // utterance are processed in K chunks [j_c, j_c+1): the main stream computes LPC + roots of chunk c + 1 while the side
+    // stream steps the tracker through chunk c (its state lives in est_inout), and only the last chunk's tracker — 1/K of
+    // the latency — is exposed.  Per-frame results (resonances, counts, status) are laid out [utterance][frame] as the
+    // caller sees them, so chunks touch disjoint rows; only the LPC coefficients are chunk-local (written and consumed on
+    // the main stream).  VBX_FORMANT_CHUNKS=<K> overrides the choice (1 = the single pass).
+    int K = 1;
+    if (track) {
+        K = 8;
+        if (J / 32 < K) K = (int)(J / 32);
+        if (F / 65536 < K) K = (int)(F / 65536);
+        if (const char* e = getenv("VBX_FORMANT_CHUNKS")) K = atoi(e);
+        if (K > J) K = (int)J;
+        if (K < 1) K = 1;
+    }
+    cudaStream_t side_stream = ctx->s_side;
+    if (const char* e = getenv("VBX_FORMANT_SIDE"))
+        if (e[0] == '0') side_stream = ctx->stream;
+    // chunk boundaries on multiples of 32 frames (the LPC kernels' tile): only an utterance's last tile is partial
+    auto chunk_begin = [&](int c) -> int64_t {
+        if (c <= 0) return 0;
+        if (c >= K) return J;
+        int64_t j = (J * c) / K;
+        if (J >= 64 * (int64_t)K) j = ((j + 16) / 32) * 32;
+        return j < J ? j : J;
+    };
+    int64_t Jc_max = 1;
+    for (int c = 0; c < K; ++c) Jc_max = std::max<int64_t>(Jc_max, chunk_begin(c + 1) - chunk_begin(c));
+    // scratch: lpc [segs·Jc_max][p+1] f64 | lpc status [segs·Jc_max] | status [F] | resonances [F][p] pairs | nres [F]
+    // (the last three only when the caller does not ask for them)
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t lpc_bytes = al((size_t)F * (p + 1) * sizeof(double));
-    const size_t st_bytes = al((size_t)F);
+    const int64_t Fc_max = segs * Jc_max;
+    const size_t lpc_bytes = al((size_t)Fc_max * (p + 1) * sizeof(double));
+    const size_t stl_bytes = al((size_t)Fc_max);
+    const size_t st_bytes = status_out ? 0 : al((size_t)F);
     const size_t res_es = (dtype == VBX_F64) ? 16 : 8;
     const bool own_res = (resonances_out == nullptr);
     const int R = own_res ? p : VBX_MAX_RESONANCES;
@@ -1058,8 +1141,11 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     const size_t nres_bytes = nres_out ? 0 : al((size_t)F * sizeof(int32_t));
     // the LPC stage's own scratch (Burg rows that do not fit shared memory, the r rows of the non-fused autocorrelation
     // path) is part of THIS reservation: a callee that grew the arena would free the block the pointers below point into
-    const size_t sub_bytes = al(lpc_method == VBX_LPC_BURG ? vbx_burg_scratch_bytes(ctx, frames) : vbx_lpc_scratch_bytes(ctx, frames, p + 1));
-    const size_t own_bytes = lpc_bytes + 2 * st_bytes + res_bytes + nres_bytes;
+    vbx_frames cfr = *frames;  // the largest chunk's view, for the scratch queries
+    cfr.n_frames = Fc_max;
+    cfr.frames_per_segment = Jc_max;
+    const size_t sub_bytes = al(lpc_method == VBX_LPC_BURG ? vbx_burg_scratch_bytes(ctx, &cfr) : vbx_lpc_scratch_bytes(ctx, &cfr, p + 1));
+    const size_t own_bytes = lpc_bytes + stl_bytes + st_bytes + res_bytes + nres_bytes;
     st = vbx_arena_reserve(ctx, own_bytes + sub_bytes);
     if (st != VBX_OK) return st;
     char* base = (char*)ctx->arena;
@@ -1068,37 +1154,77 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
         SubScratch(vbx_ctx* c_, void* p_, size_t b_) : c(c_) { c->sub_scratch = b_ ? p_ : nullptr; c->sub_scratch_bytes = b_; }
         ~SubScratch() { c->sub_scratch = nullptr; c->sub_scratch_bytes = 0; }
     };
-    int32_t* d_nres = nres_out ? nres_out : (int32_t*)(base + lpc_bytes + 2 * st_bytes + res_bytes);
     double* d_lpc = (double*)base;
     uint8_t* d_st_lpc = (uint8_t*)(base + lpc_bytes);
-    uint8_t* d_st = status_out ? status_out : (uint8_t*)(base + lpc_bytes + st_bytes);
-    void* d_res = own_res ? (void*)(base + lpc_bytes + 2 * st_bytes) : resonances_out;
-    const uint8_t* lpc_status = nullptr;
-    int lpc_stride, has_one;
-    {
-    SubScratch sub(ctx, base + own_bytes, sub_bytes);
-    if (lpc_method == VBX_LPC_BURG) {
-        st = vbx_lpc_burg(ctx, frames, p, d_lpc, d_st_lpc, VBX_F64);
-        lpc_status = d_st_lpc;
-        lpc_stride = p;
-        has_one = 0;
-    } else {
-        st = vbx_lpc(ctx, frames, p, nullptr, d_lpc, nullptr, VBX_F64);
-        lpc_stride = p + 1;
-        has_one = 1;
+    uint8_t* d_st = status_out ? status_out : (uint8_t*)(base + lpc_bytes + stl_bytes);
+    void* d_res = own_res ? (void*)(base + lpc_bytes + stl_bytes + st_bytes) : resonances_out;
+    int32_t* d_nres = nres_out ? nres_out : (int32_t*)(base + lpc_bytes + stl_bytes + st_bytes + res_bytes);
+    const size_t es = vbx_dtype_size(frames->dtype);
+    const int64_t seg_stride = frames->frames_per_segment > 0 ? frames->segment_stride : 0;
+    for (int c = 0; c < K; ++c) {
+        const int64_t j0 = chunk_begin(c), j1 = chunk_begin(c + 1), Jc = j1 - j0;
+        if (Jc <= 0) continue;
+        vbx_frames sub = *frames;
+        sub.base = (const char*)frames->base + (size_t)j0 * frames->frame_stride * es;
+        sub.n_frames = segs * Jc;
+        sub.frames_per_segment = (K > 1 || frames->frames_per_segment > 0) ? Jc : 0;
+        sub.segment_stride = seg_stride;
+        const uint8_t* lpc_status = nullptr;
+        int lpc_stride, has_one;
+        {
+            SubScratch scoped(ctx, base + own_bytes, sub_bytes);
+            if (lpc_method == VBX_LPC_BURG) {
+                st = vbx_lpc_burg(ctx, &sub, p, d_lpc, d_st_lpc, VBX_F64);
+                lpc_status = d_st_lpc;
+                lpc_stride = p;
+                has_one = 0;
+            } else {
+                // the persistent LPC kernel leaves SMs for the co-running tracker: 16 of its warps (512 utterances) per SM
+                ctx->reserve_sms = (track && K > 1 && side_stream != ctx->stream) ? (int)((segs + kTrkThreadsPacked - 1) / kTrkThreadsPacked) : 0;
+                if (const char* e = getenv("VBX_FORMANT_RESERVE_SMS")) ctx->reserve_sms = atoi(e);
+                st = vbx_lpc(ctx, &sub, p, nullptr, d_lpc, nullptr, VBX_F64);
+                ctx->reserve_sms = 0;
+                lpc_stride = p + 1;
+                has_one = 1;
+            }
+        }
+        if (st != VBX_OK) break;
+        st = lpc_to_resonances_impl(ctx, d_lpc, VBX_F64, sub.n_frames, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
+                                    d_res, R, d_nres, nullptr, d_st, dtype, -1, K > 1 ? Jc : 0, K > 1 ? J : 0, K > 1 ? j0 : 0);
+        if (st != VBX_OK) break;
+        if (!track) continue;
+        if (K == 1) {
+            st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, segs, J, d_st, est_inout, n_formants, tracks_out, dtype,
+                                        d_nres);
+            if (st != VBX_OK) break;
+            continue;
+        }
+        if (side_stream == ctx->stream) {  // VBX_FORMANT_SIDE=0 (A/B runs): chunks without overlap
+            st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, segs, J, d_st, est_inout, n_formants, tracks_out, dtype,
+                                        d_nres, j0, Jc);
+            if (st != VBX_OK) break;
+            continue;
+        }
+        // chunk c's resonances are ready -> its tracker steps on the side stream (after chunk c − 1's: same stream)
+        cudaEvent_t ready = ctx->ev_side[c & 1];
+        if (cudaEventRecord(ready, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->s_side, ready, 0) != cudaSuccess) {
+            st = vbx_fail(ctx, VBX_ERR_CUDA, "find_formants: chunk hand-over failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, segs, J, d_st, est_inout, n_formants, tracks_out, dtype,
+                                    d_nres, j0, Jc, side_stream);
+        if (st != VBX_OK) break;
     }
+    if (track && K > 1 && side_stream != ctx->stream) {
+        // join: whatever follows on the context's stream (and vbx_sync) sees the tracks and the final state.  Done on the
+        // error path too, so the side stream never runs behind the caller's back.
+        cudaEvent_t done = ctx->ev_side[2];
+        if (cudaEventRecord(done, ctx->s_side) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, done, 0) != cudaSuccess) {
+            if (st == VBX_OK) st = vbx_fail(ctx, VBX_ERR_CUDA, "find_formants: join failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (ctx->prof_on) vbx_prof_mark(ctx, "(wait: last chunk's tracker)");
     }
-    if (st != VBX_OK) return st;
-    st = vbx_lpc_to_resonances(ctx, d_lpc, VBX_F64, F, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
-                               d_res, R, d_nres, nullptr, d_st, dtype, -1);
-    if (st != VBX_OK) return st;
-    if (n_formants > 0 && est_inout) {
-        const int64_t J = vbx_frames_per_segment(frames);
-        st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, F / J, J, d_st, est_inout, n_formants, tracks_out, dtype,
-                                    d_nres);
-        if (st != VBX_OK) return st;
-    }
-    return VBX_OK;
+    return st;
 }
 
 }  // extern "C"

@@ -40,6 +40,10 @@ struct vbx_ctx {
     cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* pipe = nullptr;
     size_t pipe_bytes = 0;
+    // side stream of vbx_find_formants (the latency-bound tracker of frame chunk c runs there while the main stream computes
+    // the LPC / roots of chunk c + 1); ev_side: [0..1] chunk c's resonances ready, [2..3] chunk c's tracker done, by chunk parity
+    cudaStream_t s_side = nullptr;
+    cudaEvent_t ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
     // window tables (device, f64), keyed by (kind << 32 | n)
     std::map<uint64_t, double*> windows;
     // per-kernel timing (vbx_profile_*): an event after every launch; a kernel's time = the gap to the previous event
@@ -48,9 +52,14 @@ struct vbx_ctx {
     std::vector<const char*> prof_names;    // name of the launch that precedes event i+1 (event 0 = begin marker)
     size_t prof_used = 0;
     std::map<std::string, std::pair<double, int64_t>> prof_totals;  // name -> (ms, launches)
+    // launches on the side stream are timed as explicit (start, stop) event pairs on that stream
+    struct ProfRange { const char* name; cudaEvent_t e0, e1; };
+    std::vector<ProfRange> prof_ranges;
     // executed-work counters of the data-dependent kernels (device, VBX_N_WORK_COUNTERS × u64; zeroed by vbx_profile_begin,
     // incremented only while profiling is on): see vbx_profile_counters in the header
     unsigned long long* work_counters = nullptr;
+    int reserve_sms = 0;               // SMs the persistent kernels leave free for a co-running side-stream kernel
+    unsigned* tile_counter = nullptr;  // device: the persistent kernels' dynamic tile cursor (zeroed before every launch)
     vbx_mfcc_cache* mfcc_cache = nullptr;
     bool mfcc_fft_f32 = false;  // MFCC transform precision (default fp64)
 };
@@ -61,6 +70,9 @@ static inline unsigned long long* vbx_work_ptr(vbx_ctx* ctx) { return ctx->prof_
 
 int vbx_fail(vbx_ctx* ctx, int status, const char* fmt, ...);
 void vbx_prof_mark(vbx_ctx* ctx, const char* name);        // records "launch `name` was just enqueued" (profiling on)
+// side-stream launches: begin returns a slot (or -1), end closes it; counts the launch
+int vbx_prof_range_begin(vbx_ctx* ctx, const char* name, cudaStream_t stream);
+void vbx_prof_range_end(vbx_ctx* ctx, int slot, cudaStream_t stream);
 int vbx_arena_reserve(vbx_ctx* ctx, size_t bytes);         // ensures ctx->arena has >= bytes
 int vbx_pinned_reserve(vbx_ctx* ctx, size_t bytes);        // ensures ctx->pinned has >= bytes
 // scratch for a kernel launcher: the caller-provided sub-range if one is set (see vbx_ctx::sub_scratch), else the arena

@@ -15,6 +15,7 @@
 // memory and the results leave through a coalesced store.
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "vbx_internal.cuh"
 #include "vbx_pipeline.cuh"
@@ -320,7 +321,14 @@ __global__ void __launch_bounds__(kMaxThreads, (L <= 13 ? 5 : 1)) lpc_fused_kern
     lpc_finish<L>(P, acc, g < Gc && q == 0, g, Gc, g0, s_out);
 }
 
+// VBX_LPC_FORCE_GENERIC=1 (tests): no fused kernel, the generic autocorrelation + stand-alone Levinson run instead
+bool lpc_force_generic() {
+    const char* e = getenv("VBX_LPC_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
+
 #include "vbx_lpc16.cuh"
+#include "vbx_lpca.cuh"
 
 // Generic fallback (any n_lags / frame length): one CTA per frame, windowed frame as fp64 in
 // shared memory when it fits, lags strided over warps with a shuffle reduction.
@@ -431,6 +439,46 @@ template <typename TIn> struct LpcTable<TIn, 1> {
     static void fill(lpc_kernel_t*) {}
 };
 
+typedef void (*lpca_kernel_t)(const LpcParams, const LpcaExtra);
+template <typename TIn, int L> struct LpcaTable {
+    static void fill(lpca_kernel_t* t) {
+        t[L] = lpc_fuseda_kernel<L, TIn>;
+        LpcaTable<TIn, L - 1>::fill(t);
+    }
+};
+template <typename TIn> struct LpcaTable<TIn, 1> {
+    static void fill(lpca_kernel_t*) {}
+};
+
+// The two shifted window rows of lpc_fuseda_kernel, E = [0, 0, w…, 0…] and O = [0, 0, 0, w…, 0…] ([2][wt] f64), cached per
+// (window kind, n, sample dtype) next to the plain tables.
+int get_window_rows_aligned(vbx_ctx* ctx, int kind, int n, int wt, const double** dev_out, int sample_dtype) {
+    const bool pcm = (sample_dtype == VBX_I16);
+    const uint64_t key = ((uint64_t)(uint32_t)(kind | (pcm ? 0x100 : 0) | 0x200) << 32) | (uint32_t)n;
+    auto it = ctx->windows.find(key);
+    if (it != ctx->windows.end()) {
+        *dev_out = it->second;
+        return VBX_OK;
+    }
+    std::vector<double> w(n), rows((size_t)2 * wt, 0.0);
+    vbx_window_fill_host(kind, n, w.data());
+    for (int i = 0; i < n; ++i) {
+        const double v = pcm ? w[i] / 32767.0 : w[i];
+        rows[(size_t)2 + i] = v;        // E
+        rows[(size_t)wt + 3 + i] = v;   // O
+    }
+    double* dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, rows.size() * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return vbx_fail(ctx, VBX_ERR_NOMEM, "window rows: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    VBX_CUDA(ctx, cudaMemcpy(dev, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->windows[key] = dev;
+    *dev_out = dev;
+    return VBX_OK;
+}
+
 template <typename TIn, int L> struct Lpc16Table {
     static void fill(lpc_kernel_t* t) {
         t[L] = lpc_fused16_kernel<L, TIn>;
@@ -456,12 +504,6 @@ constexpr int kMaxLevinsonOrder = 32;
 // Choose lanes-per-frame K (and the CTA size): the smallest power of two whose CTA span fits the
 // shared-memory budget, keeping each lane's part >= 2L samples.  Returns false if no fused
 // configuration fits.  VBX_LPC_PLAN="k:threads" overrides the choice (tuning experiments).
-// VBX_LPC_FORCE_GENERIC=1 (tests): no fused kernel, the generic autocorrelation + stand-alone Levinson run instead
-bool lpc_force_generic() {
-    const char* e = getenv("VBX_LPC_FORCE_GENERIC");
-    return e && e[0] == '1';
-}
-
 bool plan_fused(const vbx_ctx* ctx, int n, int64_t stride, int L, LpcParams* P, size_t* smem_bytes) {
     if (lpc_force_generic()) return false;
     const int sv = (int)(stride < (int64_t)n ? stride : n);
@@ -582,9 +624,13 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     struct Tables {
         lpc_kernel_t general[kMaxFastLags + 1] = {nullptr};
         lpc_kernel_t chunk16[kChunk + 1] = {nullptr};
+        lpca_kernel_t aligned[kLpcaMaxLags + 1] = {nullptr};
+        lpcp_kernel_t persistent[kLpcaMaxLags + 1] = {nullptr};
         Tables() {
             LpcTable<TIn, kMaxFastLags>::fill(general);
             Lpc16Table<TIn, kChunk>::fill(chunk16);
+            LpcaTable<TIn, kLpcaMaxLags>::fill(aligned);
+            if (std::is_same<TIn, float>::value) LpcpTable<kLpcaMaxLags>::fill(persistent);
         }
     };
     static const Tables tables;
@@ -595,6 +641,47 @@ int launch_lpc(vbx_ctx* ctx, const vbx_frames* fr, int L, void* r_out, void* ac_
     memset(&P, 0, sizeof(P));
     size_t smem = 0;
     const bool fused16 = plan_fused16(ctx, fr->frame_len, fr->frame_stride, vbx_frames_per_segment(fr), L, &P, &smem);
+    LpcaExtra X;
+    memset(&X, 0, sizeof(X));
+    int n_tiles = 0;
+    bool persistent = false;
+    if constexpr (std::is_same<TIn, float>::value) persistent = !fused16 && plan_fusedp(ctx, fr, L, &P, &X, &smem, &n_tiles);
+    if (persistent || (!fused16 && plan_fuseda(ctx, fr->frame_len, fr->frame_stride, L, sizeof(TIn), &P, &X, &smem))) {
+        // any other overlapped / packed framing with <= 13 lags: the aligned-down 16-sample-chunk walk (vbx_lpca.cuh)
+        st = get_window_rows_aligned(ctx, fr->window, fr->frame_len, X.wt, &X.tabs, fr->dtype);
+        if (st != VBX_OK) return st;
+        P.base = fr->base;
+        P.win = win;
+        P.r_out = r_out;
+        P.ac_out = ac_out;
+        P.kc_out = kc_out;
+        P.n_frames = fr->n_frames;
+        P.stride = fr->frame_stride;
+        P.seg_frames = vbx_frames_per_segment(fr);
+        P.seg_stride = fr->frames_per_segment > 0 ? fr->segment_stride : 0;
+        P.ctas_per_seg = (int)((P.seg_frames + P.frames_per_cta - 1) / P.frames_per_cta);
+        P.n = fr->frame_len;
+        P.out_f64 = (out_dtype == VBX_F64);
+        P.do_levinson = do_levinson ? 1 : 0;
+        if (persistent) {
+            // enough tiles for every SM: the persistent, TMA-fed, warp-specialised CTA (one per SM)
+            lpcp_kernel_t kern = tables.persistent[L];
+            VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = ctx->sm_count - (ctx->reserve_sms > 0 && ctx->reserve_sms < ctx->sm_count / 2 ? ctx->reserve_sms : 0);
+            if (n_tiles < grid) grid = n_tiles;
+            VBX_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned), ctx->stream));
+            kern<<<(unsigned)grid, P.threads, smem, ctx->stream>>>(P, X, n_tiles, ctx->tile_counter);
+            VBX_CHECK_LAUNCH(ctx, "lpc_fusedp_kernel");
+            return VBX_OK;
+        }
+        lpca_kernel_t kern = tables.aligned[L];
+        VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t grid = (fr->n_frames / P.seg_frames) * P.ctas_per_seg;
+        VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
+        kern<<<(unsigned)grid, P.threads, smem, ctx->stream>>>(P, X);
+        VBX_CHECK_LAUNCH(ctx, "lpc_fuseda_kernel");
+        return VBX_OK;
+    }
     const bool fused_ok =
         fused16 || ((L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem));
     if (fused_ok) {
@@ -665,6 +752,8 @@ bool lpc_is_fused(vbx_ctx* ctx, const vbx_frames* fr, int L) {
     memset(&P, 0, sizeof(P));
     size_t smem = 0;
     if (plan_fused16(ctx, fr->frame_len, fr->frame_stride, vbx_frames_per_segment(fr), L, &P, &smem)) return true;
+    LpcaExtra X;
+    if (plan_fuseda(ctx, fr->frame_len, fr->frame_stride, L, vbx_dtype_size(fr->dtype), &P, &X, &smem)) return true;
     return (L >= 2 && L <= kMaxFastLags) && plan_fused(ctx, fr->frame_len, fr->frame_stride, L, &P, &smem);
 }
 

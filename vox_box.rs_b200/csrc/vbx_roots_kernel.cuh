@@ -44,6 +44,9 @@ struct RootsParams {
     int strict_im;         // 1: keep roots with im > 0 (lib.rs:95), 0: im >= 0 (to_resonance)
     int polish_steps;
     unsigned long long* work;  // executed-work counters (vbx_profile_counters) or null
+    // vbx_find_formants runs the frames of every utterance in chunks: input row f (chunk-local, in_J frames per utterance) is
+    // output row (f / in_J)·out_J + out_j0 + f % in_J of the caller's [utterance][frame] layout.  out_J == 0: identity.
+    int64_t in_J, out_J, out_j0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -96,23 +99,24 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     const int tid = threadIdx.x;
     const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
     const bool in_range = f_raw < Q.n_frames;
-    const int64_t f = in_range ? f_raw : Q.n_frames - 1;  // out-of-range lanes shadow the last frame (no stores): warp-wide ops stay full
+    const int64_t f = in_range ? f_raw : Q.n_frames - 1;
+    const int64_t fo = Q.out_J ? (f / Q.in_J) * Q.out_J + Q.out_j0 + (f % Q.in_J) : f;  // output row  // out-of-range lanes shadow the last frame (no stores): warp-wide ops stay full
     const int R = Q.R;
     auto write_res = [&](int slot, double fr_, double bw_) {
         if (Q.out_f64) {
-            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)fo * R + slot) * 2;
             o[0] = fr_; o[1] = bw_;
         } else {
-            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)fo * R + slot) * 2;
             o[0] = (float)fr_; o[1] = (float)bw_;
         }
     };
     auto write_root = [&](int k, vcx<double> z) {
         if (Q.out_f64) {
-            double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+            double* o = reinterpret_cast<double*>(Q.roots_out) + ((size_t)fo * P + k) * 2;
             o[0] = z.re; o[1] = z.im;
         } else {
-            float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)f * P + k) * 2;
+            float* o = reinterpret_cast<float*>(Q.roots_out) + ((size_t)fo * P + k) * 2;
             o[0] = (float)z.re; o[1] = (float)z.im;
         }
     };
@@ -191,8 +195,8 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     }
     if (lpc_failed) {
         if (in_range) {
-            if (Q.status_out) Q.status_out[f] = Q.status_in[f];
-            if (Q.nres_out) Q.nres_out[f] = 0;
+            if (Q.status_out) Q.status_out[fo] = Q.status_in[f];
+            if (Q.nres_out) Q.nres_out[fo] = 0;
             if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
         }
         return;
@@ -248,8 +252,8 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
             ++cnt;
         }
     }
-    if (Q.status_out) Q.status_out[f] = VBX_OK;  // NaN/inf roots yield no resonance, silently, as in the reference
-    if (Q.nres_out) Q.nres_out[f] = cnt;
+    if (Q.status_out) Q.status_out[fo] = VBX_OK;  // NaN/inf roots yield no resonance, silently, as in the reference
+    if (Q.nres_out) Q.nres_out[fo] = cnt;
     if (Q.res_out) {
         // stable rank sort by frequency (lib.rs:105-110 / spectrum.rs:207), zero padding behind
 #pragma unroll 1
@@ -296,13 +300,14 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
     const bool in_range = f_raw < Q.n_frames;
     const int64_t f = in_range ? f_raw : Q.n_frames - 1;
+    const int64_t fo = Q.out_J ? (f / Q.in_J) * Q.out_J + Q.out_j0 + (f % Q.in_J) : f;  // output row
     const int R = Q.R;
     auto write_res = [&](int slot, double fr_, double bw_) {
         if (Q.out_f64) {
-            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            double* o = reinterpret_cast<double*>(Q.res_out) + ((size_t)fo * R + slot) * 2;
             o[0] = fr_; o[1] = bw_;
         } else {
-            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)f * R + slot) * 2;
+            float* o = reinterpret_cast<float*>(Q.res_out) + ((size_t)fo * R + slot) * 2;
             o[0] = (float)fr_; o[1] = (float)bw_;
         }
     };
@@ -405,8 +410,8 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     }
     if (lpc_failed) {
         if (in_range) {
-            if (Q.status_out) Q.status_out[f] = Q.status_in[f];
-            if (Q.nres_out) Q.nres_out[f] = 0;
+            if (Q.status_out) Q.status_out[fo] = Q.status_in[f];
+            if (Q.nres_out) Q.nres_out[fo] = 0;
             if (Q.res_out) for (int s = 0; s < R; ++s) write_res(s, 0.0, 0.0);
         }
         return;
@@ -459,8 +464,8 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
             ++cnt;
         }
     }
-    if (Q.status_out) Q.status_out[f] = VBX_OK;
-    if (Q.nres_out) Q.nres_out[f] = cnt;
+    if (Q.status_out) Q.status_out[fo] = VBX_OK;
+    if (Q.nres_out) Q.nres_out[fo] = cnt;
     if (Q.res_out) {
 #pragma unroll 1
         for (int k = 0; k < cnt; ++k) {
