@@ -991,7 +991,7 @@ int vbx_roots_to_resonances(vbx_ctx* ctx, const void* roots, int32_t dtype, int6
 static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t res_dtype, int32_t res_slots, int32_t n_resonances,
                                   int64_t n_segments, int64_t frames_per_segment, const uint8_t* status_in, void* est_inout,
                                   int32_t n_estimates, void* tracks_out, int32_t dtype, const int32_t* nres,
-                                  int64_t j_begin = 0, int64_t j_count = -1, cudaStream_t stream = nullptr) {
+                                  int64_t j_begin = 0, int64_t j_count = -1, cudaStream_t stream = nullptr, bool packed = false) {
     if (!ctx) return VBX_ERR_BADARG;
     if (!stream) stream = ctx->stream;
     if (j_count < 0) j_count = frames_per_segment - j_begin;
@@ -1018,13 +1018,14 @@ static int estimate_formants_impl(vbx_ctx* ctx, const void* resonances, int32_t 
     const char* tv = getenv("VBX_TRACKER");
     const bool aligned = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(resonances) & 15) == 0);
     const int chunks = (int)(row_bytes / 16);
-    // On vbx_find_formants' side stream the tracker runs next to the LPC / roots grids of the following frame chunk.  With its
-    // small CTAs spread over every SM, each of its warps competes with 8-16 busy warps for issue slots and the (purely
-    // latency-bound) step chain runs 4-5x slower — slower than the main stream's chunk, so the tracker became the critical path
-    // (measured: 1.2 ms per chunk against 0.27 alone).  The persistent LPC kernel therefore leaves a few SMs free
-    // (ctx->reserve_sms): the block scheduler puts the tracker's CTAs there, 8 per SM, where they keep the issue slots largely
-    // to themselves (0.66 ms per chunk, hidden).  VBX_TRACKER_THREADS packs it into bigger CTAs (A/B runs: no better).
-    int trk_threads = kTrkThreads;
+    // On vbx_find_formants' side stream the tracker runs next to the LPC / roots grids of the following frame chunk.  Spread as
+    // 64-thread CTAs over every SM, each of its warps competes with 8-16 busy warps for issue slots and the (purely latency-
+    // bound) step chain runs 4-5x slower — slower than the main stream's chunk, so the tracker became the critical path
+    // (measured: 1.2 ms per chunk against 0.27 alone).  `packed` launches it as 512-thread CTAs instead: ~n_segments / 512 of
+    // them, each filling most of an SM's shared memory, so they cannot share an SM with the persistent LPC kernel's CTA — which
+    // leaves exactly that many SMs free (ctx->reserve_sms).  Whichever kernel the block scheduler places first, the tracker ends
+    // up alone on its SMs (0.69 ms per chunk, hidden); with small CTAs the outcome depended on the launch race.
+    int trk_threads = packed ? kTrkThreadsPacked : kTrkThreads;
     if (const char* e = getenv("VBX_TRACKER_THREADS")) {
         const int v = atoi(e);
         if (v >= 32 && v <= kTrkThreadsPacked && v % 32 == 0) trk_threads = v;
@@ -1211,8 +1212,9 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
             st = vbx_fail(ctx, VBX_ERR_CUDA, "find_formants: chunk hand-over failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        // (the last chunk's tracker has the device to itself: small CTAs over all SMs, 0.27 ms instead of 0.69)
         st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, segs, J, d_st, est_inout, n_formants, tracks_out, dtype,
-                                    d_nres, j0, Jc, side_stream);
+                                    d_nres, j0, Jc, side_stream, /*packed=*/c + 1 < K);
         if (st != VBX_OK) break;
     }
     if (track && K > 1 && side_stream != ctx->stream) {
