@@ -111,6 +111,7 @@ def _declare(L):
         _dp, _i64, _dp, _dp, _i32p, _dp, _u8p, C.c_int)
     sig("vbo_batch_pitch", C.c_int, _fp, _i64, _i64, _i64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
         _dp, _i64, _i32p, _u8p, C.c_int)
+    sig("vbo_laguerre_stats", None, _i64p, C.c_int)
     sig("vbo_batch_pitch_variant", C.c_int, _fp, _i64, _i64, _i64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
         _dp, _i64, _i32p, _u8p, C.c_int)
     sig("vbo_batch_mfcc", C.c_int, _fp, _i64, _i64, _i64, C.c_int, _i64, C.c_double, C.c_double, C.c_double, _i64,
@@ -454,6 +455,13 @@ def batch_pitch(audio, n_frames, frame_len, stride, window, fs, threshold, fmin,
     lib().vbo_batch_pitch(_f(a), n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, _d(cand), max_cand,
                           nc.ctypes.data_as(_i32p), st.ctypes.data_as(_u8p), n_threads)
     return cand, nc, st
+
+
+def laguerre_stats(reset=True):
+    """(solves, solves that ran all 20 iterations, of those not converged) since the last reset — polynomial.rs:34-72."""
+    out = np.zeros(3, dtype=np.int64)
+    lib().vbo_laguerre_stats(out.ctypes.data_as(_i64p), int(reset))
+    return tuple(int(v) for v in out)
 
 
 def batch_pitch_variant(audio, n_frames, frame_len, stride, window, fs, threshold, fmin, fmax, acf_variant, max_cand=16, n_threads=1):

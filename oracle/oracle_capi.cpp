@@ -326,6 +326,16 @@ VBO_API int vbo_batch_pitch(const float* base, int64_t n_frames, int64_t n, int6
     return OK;
 }
 
+// Laguerre statistics since the last reset: out[0] solves, out[1] solves that ran all 20 iterations, out[2] of those the ones
+// whose last update was still > 1e-8·max(1, |z|) (not converged).  reset != 0 clears the counters after reading.
+VBO_API void vbo_laguerre_stats(int64_t* out, int reset) {
+    LaguerreStats& st = laguerre_stats();
+    out[0] = st.solves.load();
+    out[1] = st.capped.load();
+    out[2] = st.unconverged.load();
+    if (reset) { st.solves = 0; st.capped = 0; st.unconverged = 0; }
+}
+
 // the same loop with a rounding-level variant of the autocorrelation fold (tools/pitch_sensitivity.py)
 VBO_API int vbo_batch_pitch_variant(const float* base, int64_t n_frames, int64_t n, int64_t stride, int window_kind,
                                     double fs, double threshold, double fmin, double fmax, int acf_variant,

@@ -21,6 +21,7 @@
 // are marked "parity unpinned" where they are used.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -265,10 +266,22 @@ template <class T> size_t poly_off_low(const Cx<T>* c, size_t len) {
 // polynomial.rs:34-72 laguerre.  n = len-1 of the SLICE (never the deflated
 // degree); c1 = sqrt((n-1)·n·cb − ca2); ≤20 iterations; exit only if |P| ≤ 1e-16.
 // *iters (optional) receives the number of completed update steps.
+// Statistics over every solve since the last reset (test infrastructure: tools/parity_scale.py counts the frames on which
+// the reference's own 20-iteration cap leaves a NON-root — it then deflates by that non-root, and parity must copy the
+// result): solves, solves that ran all 20 iterations, and of those the ones whose last update was still larger than
+// 1e-8·max(1, |z|), i.e. not converged.
+struct LaguerreStats {
+    std::atomic<long long> solves{0}, capped{0}, unconverged{0};
+};
+inline LaguerreStats& laguerre_stats() {
+    static LaguerreStats s;
+    return s;
+}
 template <class T> Cx<T> laguerre(const Cx<T>* c, size_t len, Cx<T> start, int* iters = nullptr) {
     size_t n = len - 1;
     Cx<T> z = start;
     int it = 0;
+    double last_step = 0.0;
     for (; it < 20; ++it) {
         Cx<T> abg0 = c[n], abg1, abg2;
         for (size_t j = n; j-- > 0;) {
@@ -285,6 +298,16 @@ template <class T> Cx<T> laguerre(const Cx<T>* c, size_t len, Cx<T> start, int* 
         Cx<T> cc2 = ca - c1;
         Cx<T> cc = (norm(cc1) > norm(cc2)) ? Cx<T>(T(double(n))) / cc1 : Cx<T>(T(double(n))) / cc2;
         z = z + cc;
+        last_step = std::sqrt(double(cc.re) * double(cc.re) + double(cc.im) * double(cc.im));
+    }
+    {
+        LaguerreStats& st = laguerre_stats();
+        st.solves.fetch_add(1, std::memory_order_relaxed);
+        if (it == 20) {
+            st.capped.fetch_add(1, std::memory_order_relaxed);
+            const double za = std::sqrt(double(z.re) * double(z.re) + double(z.im) * double(z.im));
+            if (!(last_step <= 1e-8 * (za > 1.0 ? za : 1.0))) st.unconverged.fetch_add(1, std::memory_order_relaxed);
+        }
     }
     if (iters) *iters = it;
     return z;
