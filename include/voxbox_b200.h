@@ -141,7 +141,8 @@ VBX_API int vbx_profile_entry(vbx_ctx* ctx, int index, char* name_out, int name_
 /* Executed-work counters of the data-dependent kernels, accumulated between vbx_profile_begin and vbx_profile_end (zero
  * outside): out[0] = Horner coefficient steps and out[1] = Laguerre rounds executed by lpc_roots_pair_kernel, summed over
  * lanes (a warp runs every round at its largest live degree, so idle lanes' steps are counted: executed, not useful, work);
- * out[2] = term-loop iterations and out[3] = interpolant evaluations executed by pitch_refine8q_kernel, summed over lanes.
+ * out[2] = term-loop iterations and out[3] = interpolant evaluations executed by pitch_refine8q_kernel, summed over lanes;
+ * out[4] = frames the pair kernel handed to the f64 fix-up launch (a Laguerre solve hit the 20-iteration cap unconverged).
  * bench.py turns them into executed flop for the roofline fractions of those kernels.  Synchronises.  n <= 8. */
 VBX_API int vbx_profile_counters(vbx_ctx* ctx, uint64_t* out, int32_t n);
 

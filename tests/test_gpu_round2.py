@@ -451,3 +451,29 @@ def test_lpc_persistent_kernel_nonfinite_and_alignment(oracle, monkeypatch):
             assert np.array_equal(np.isnan(sl), np.isnan(rr)), (off, u)
             ok = np.isfinite(rr).all(axis=1)
             assert np.max(normwise(sl[ok], rr[ok])) < 1e-12, (off, u)
+
+
+# ------------------------------------------------------------------------------------- roots fix-up launch
+def test_roots_fixup_redoes_flagged_frames_in_f64(oracle, monkeypatch):
+    """Frames on which the pair-deflation kernel's Laguerre solve runs into the 20-iteration cap without converging are redone by
+    the f64 reference-order kernel.  VBX_ROOTS_FORCE_HARD=7 flags every 7th frame: those rows must equal the precision = 1 path bit
+    for bit, the others the unflagged pair result."""
+    c = ctx()
+    fs, N, hop = 44100, 1102, 441
+    d = c.synth_speech(2, fs * 2, fs, first_utt=3131)
+    J = c.n_frames_of(fs * 2, N, hop)
+    fr = c.frames(d.ptr, 2 * J, N, hop, vb.WINDOW_HANN_SYMMETRIC, frames_per_segment=J, segment_stride=fs * 2)
+    r, ac, _ = c.lpc(fr, 12)
+    pair = c.lpc_to_resonances(ac, 12, True, float(fs))
+    f64 = c.lpc_to_resonances(ac, 12, True, float(fs), precision=1)
+    monkeypatch.setenv("VBX_ROOTS_FORCE_HARD", "7")
+    c.profile_begin()
+    mixed = c.lpc_to_resonances(ac, 12, True, float(fs))
+    names = c.profile_end()
+    assert "lpc_roots_pair_kernel" in names and "lpc_roots_fixup_kernel" in names
+    a, b, m = pair["resonances"].to_host(), f64["resonances"].to_host(), mixed["resonances"].to_host()
+    flagged = (np.arange(2 * J) % 7) == 0
+    assert np.array_equal(m[flagged], b[flagged])
+    assert np.array_equal(m[~flagged], a[~flagged])
+    assert np.array_equal(mixed["n_res"].to_host(), pair["n_res"].to_host())
+    assert np.max(np.abs(a - b)) < 1e-3  # and the two solvers agree anyway

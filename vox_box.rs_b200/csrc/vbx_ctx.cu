@@ -273,6 +273,7 @@ int vbx_ctx_create(int device, vbx_ctx** out) {
             return VBX_ERR_CUDA;
         }
     if (cudaMalloc(&ctx->tile_counter, 256) != cudaSuccess) { delete ctx; return VBX_ERR_CUDA; }
+    if (cudaMalloc(&ctx->hard_list, vbx_ctx::kHardCap * sizeof(int)) != cudaSuccess) { delete ctx; return VBX_ERR_CUDA; }
     {
         // the tracker's CTAs should be dispatched ahead of the queued LPC / roots grids: highest priority
         int lo = 0, hi = 0;
@@ -294,6 +295,7 @@ int vbx_ctx_destroy(vbx_ctx* ctx) {
     for (auto e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->work_counters) cudaFree(ctx->work_counters);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
+    if (ctx->hard_list) cudaFree(ctx->hard_list);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pipe) cudaFree(ctx->pipe);

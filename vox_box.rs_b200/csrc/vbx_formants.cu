@@ -254,7 +254,37 @@ int launch_burg(vbx_ctx* ctx, const vbx_frames* fr, int p, void* coeffs_out, uin
 // =============================================================================================
 using namespace vbx_roots;
 
-int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*0 fast f32+polish, 1 f64*/) {
+// The f64 fix-up launch behind lpc_roots_pair_kernel (see there): redoes the frames of ctx->hard_list with the reference's own
+// algorithm.  Covers the list's capacity; CTAs beyond the list's length return at once (an empty list costs a few µs, a flagged
+// frame ~0.25 ms of single-thread latency — which is why vbx_find_formants puts this launch on its side stream).
+int launch_roots_fixup(vbx_ctx* ctx, const RootsParams& Q, int p, cudaStream_t stream) {
+    RootsParams Q2 = Q;
+    Q2.frame_list = ctx->hard_list;
+    Q2.frame_count = ctx->tile_counter + 1;
+    Q2.hard_cap = vbx_ctx::kHardCap;
+    Q2.hard_list = nullptr;
+    Q2.hard_count = nullptr;
+    Q2.work = nullptr;
+    const size_t smem_fix = roots_rt_smem_bytes(p, false);
+    VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_rt_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fix));
+    const bool side = (stream != ctx->stream);
+    const int slot = side ? vbx_prof_range_begin(ctx, "lpc_roots_fixup_kernel", stream) : -1;
+    lpc_roots_rt_kernel<double><<<vbx_ctx::kHardCap / kRootsThreads, kRootsThreads, smem_fix, stream>>>(Q2, p);
+    if (side) {
+        vbx_prof_range_end(ctx, slot, stream);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "launch of lpc_roots_fixup_kernel failed: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    } else {
+        VBX_CHECK_LAUNCH(ctx, "lpc_roots_fixup_kernel");
+    }
+    return VBX_OK;
+}
+
+// defer_fixup (out, optional): when given, the pair path does NOT launch its fix-up; *defer_fixup tells the caller to do so
+// (launch_roots_fixup with the same parameters) once the pair kernel's results are visible to the stream of its choice.
+int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*0 fast f32+polish, 1 f64*/, bool* defer_fixup = nullptr) {
+    if (defer_fixup) *defer_fixup = false;
     VBX_REQUIRE(ctx, p >= 2 && p <= kMaxRootsOrder, "LPC order for root finding must be in 2..%d", kMaxRootsOrder);
     const int64_t grid = (Q.n_frames + kRootsThreads - 1) / kRootsThreads;
     VBX_REQUIRE(ctx, grid <= 0x7fffffffLL, "too many frames for one launch");
@@ -265,9 +295,22 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
     if (f32 && !Q.roots_out && !(pe && pe[0] == '0')) {
         const size_t smem_pair = roots_pair_smem_bytes(p);
         VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
-        lpc_roots_pair_kernel<<<(unsigned)grid, kRootsThreads, smem_pair, ctx->stream>>>(Q, p);
+        RootsParams Q1 = Q;
+        Q1.work = vbx_work_ptr(ctx);
+        Q1.hard_list = ctx->hard_list;
+        Q1.hard_count = ctx->tile_counter + 1;
+        Q1.hard_cap = vbx_ctx::kHardCap;
+        if (const char* e = getenv("VBX_ROOTS_FORCE_HARD")) Q1.hard_mod = atoi(e);
+        VBX_CUDA(ctx, cudaMemsetAsync(Q1.hard_count, 0, sizeof(unsigned), ctx->stream));
+        lpc_roots_pair_kernel<<<(unsigned)grid, kRootsThreads, smem_pair, ctx->stream>>>(Q1, p);
         VBX_CHECK_LAUNCH(ctx, "lpc_roots_pair_kernel");
-        return VBX_OK;
+        // fix-up: frames on which a solve hit the 20-iteration cap twice (two start points) without converging go to the f64
+        // reference-order kernel
+        if (defer_fixup) {
+            *defer_fixup = true;
+            return VBX_OK;
+        }
+        return launch_roots_fixup(ctx, Q, p, ctx->stream);
     }
     const size_t smem = roots_rt_smem_bytes(p, f32);
     if (f32) {
@@ -880,7 +923,8 @@ int vbx_lpc_burg(vbx_ctx* ctx, const vbx_frames* frames, int32_t p, void* coeffs
 static int lpc_to_resonances_impl(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
                                   int32_t lpc_has_leading_one, double sample_rate, int32_t strict_im, const uint8_t* status_in,
                                   void* res_out, int32_t res_slots, int32_t* nres_out, void* roots_out, uint8_t* status_out,
-                                  int32_t out_dtype, int32_t precision, int64_t in_J, int64_t out_J, int64_t out_j0) {
+                                  int32_t out_dtype, int32_t precision, int64_t in_J, int64_t out_J, int64_t out_j0,
+                                  RootsParams* q_out = nullptr, bool* defer_fixup = nullptr) {
     if (!ctx) return VBX_ERR_BADARG;
     VBX_REQUIRE(ctx, lpc_dtype == VBX_F32 || lpc_dtype == VBX_F64, "lpc_dtype must be VBX_F32 or VBX_F64");
     VBX_REQUIRE(ctx, out_dtype == VBX_F32 || out_dtype == VBX_F64, "out_dtype must be VBX_F32 or VBX_F64");
@@ -898,7 +942,9 @@ static int lpc_to_resonances_impl(vbx_ctx* ctx, const void* lpc, int32_t lpc_dty
     Q.R = res_slots; Q.strict_im = strict_im ? 1 : 0; Q.polish_steps = 2;
     Q.work = vbx_work_ptr(ctx);
     Q.in_J = in_J; Q.out_J = out_J; Q.out_j0 = out_j0;
-    return launch_lpc_roots(ctx, Q, p, precision < 0 ? root_precision_default() : precision);
+    Q.hard_list = nullptr; Q.hard_count = nullptr; Q.hard_cap = 0; Q.hard_mod = 0; Q.frame_list = nullptr; Q.frame_count = nullptr;
+    if (q_out) *q_out = Q;
+    return launch_lpc_roots(ctx, Q, p, precision < 0 ? root_precision_default() : precision, defer_fixup);
 }
 
 int vbx_lpc_to_resonances(vbx_ctx* ctx, const void* lpc, int32_t lpc_dtype, int64_t n_frames, int32_t lpc_stride, int32_t p,
@@ -1190,8 +1236,12 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
             }
         }
         if (st != VBX_OK) break;
+        const bool overlap = track && K > 1 && side_stream != ctx->stream;
+        RootsParams Qc;
+        bool fixup_pending = false;
         st = lpc_to_resonances_impl(ctx, d_lpc, VBX_F64, sub.n_frames, lpc_stride, p, has_one, sample_rate, /*strict_im=*/1, lpc_status,
-                                    d_res, R, d_nres, nullptr, d_st, dtype, -1, K > 1 ? Jc : 0, K > 1 ? J : 0, K > 1 ? j0 : 0);
+                                    d_res, R, d_nres, nullptr, d_st, dtype, -1, K > 1 ? Jc : 0, K > 1 ? J : 0, K > 1 ? j0 : 0, &Qc,
+                                    overlap ? &fixup_pending : nullptr);
         if (st != VBX_OK) break;
         if (!track) continue;
         if (K == 1) {
@@ -1213,6 +1263,10 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
             break;
         }
         // (the last chunk's tracker has the device to itself: small CTAs over all SMs, 0.27 ms instead of 0.69)
+        if (fixup_pending) {  // the roots fix-up (rarely any work, but ~0.25 ms of latency when there is) rides the side stream too
+            st = launch_roots_fixup(ctx, Qc, p, side_stream);
+            if (st != VBX_OK) break;
+        }
         st = estimate_formants_impl(ctx, d_res, dtype, R, VBX_MAX_RESONANCES, segs, J, d_st, est_inout, n_formants, tracks_out, dtype,
                                     d_nres, j0, Jc, side_stream, /*packed=*/c + 1 < K);
         if (st != VBX_OK) break;

@@ -59,7 +59,9 @@ struct vbx_ctx {
     // incremented only while profiling is on): see vbx_profile_counters in the header
     unsigned long long* work_counters = nullptr;
     int reserve_sms = 0;               // SMs the persistent kernels leave free for a co-running side-stream kernel
-    unsigned* tile_counter = nullptr;  // device: the persistent kernels' dynamic tile cursor (zeroed before every launch)
+    unsigned* tile_counter = nullptr;  // device: [0] the persistent kernels' dynamic tile cursor, [1] length of hard_list
+    int* hard_list = nullptr;          // device: frames the pair-deflation roots kernel hands to the f64 fix-up launch
+    static constexpr int kHardCap = 4096;
     vbx_mfcc_cache* mfcc_cache = nullptr;
     bool mfcc_fft_f32 = false;  // MFCC transform precision (default fp64)
 };

@@ -47,6 +47,14 @@ struct RootsParams {
     // vbx_find_formants runs the frames of every utterance in chunks: input row f (chunk-local, in_J frames per utterance) is
     // output row (f / in_J)·out_J + out_j0 + f % in_J of the caller's [utterance][frame] layout.  out_J == 0: identity.
     int64_t in_J, out_J, out_j0;
+    // Frames on which a solve of the pair kernel ran into its 20-iteration cap WITHOUT converging are appended here (capacity
+    // hard_cap); the fix-up launch of the f64 reference-order kernel then redoes exactly those frames (frame_list / frame_count
+    // set: thread i works on frame frame_list[i]).  hard_mod > 0 (tests): every hard_mod-th frame is treated as hard.
+    int* hard_list;
+    unsigned* hard_count;
+    int hard_cap, hard_mod;
+    const int* frame_list;
+    const unsigned* frame_count;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,8 +105,14 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_rt_kernel(const Roots
     vcx<TR>* c_s = reinterpret_cast<vcx<TR>*>(a_s + (size_t)(P + 1) * T);   // [P+1][T] working polynomial
     vcx<TR>* r_s = c_s + (size_t)(P + 1) * T;                               // [P][T]   roots in find_roots order
     const int tid = threadIdx.x;
-    const int64_t f_raw = (int64_t)blockIdx.x * T + tid;
-    const bool in_range = f_raw < Q.n_frames;
+    int64_t f_raw = (int64_t)blockIdx.x * T + tid;
+    bool in_range = f_raw < Q.n_frames;
+    if (Q.frame_list) {  // fix-up launch: the frames the pair kernel flagged
+        const unsigned cnt = min(*Q.frame_count, (unsigned)Q.hard_cap);
+        if ((unsigned)blockIdx.x * T >= cnt) return;  // CTA-uniform
+        in_range = f_raw < (int64_t)cnt;
+        f_raw = Q.frame_list[in_range ? f_raw : 0];
+    }
     const int64_t f = in_range ? f_raw : Q.n_frames - 1;
     const int64_t fo = Q.out_J ? (f / Q.in_J) * Q.out_J + Q.out_j0 + (f % Q.in_J) : f;  // output row  // out-of-range lanes shadow the last frame (no stores): warp-wide ops stay full
     const int R = Q.R;
@@ -330,6 +344,7 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
     const vcx<TR> z_start = cmk<TR>((TR)0.3, (TR)0.9);
     vcx<TR> z = z_start;
     bool active = (P >= 3) && !lpc_failed;
+    bool hard = false, retried = false;
     unsigned work_steps = 0, work_rounds = 0;  // executed Horner steps / rounds of this lane (idle lanes run them too)
 #pragma unroll 1
     while (true) {
@@ -358,8 +373,22 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
                 // jitter around the threshold for extra iterations: 20 % more Horner work for the same roots; 1e-3 is where
                 // resonance counts start to differ — numpy emulation of this kernel, 16 and 44.1 kHz.)
                 const TR eps = (TR)1.0e-5;
-                if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) done = true;
-                if (++it == 20) done = true;
+                ++it;
+                if (cnorm_sqr(step) <= eps * eps * cnorm_sqr(z)) {
+                    done = true;
+                } else if (it == 20) {
+                    // The cap without convergence (about one frame in 10^5 on speech-like input).  Dividing a non-root out
+                    // would corrupt every later root, so first the same solve is retried from a second start point; if that
+                    // hits the cap too, the frame goes to the f64 fix-up launch (the reference's own algorithm).
+                    if (!retried) {
+                        retried = true;
+                        it = 0;
+                        z = cmk<TR>((TR)-0.4, (TR)0.85);
+                    } else {
+                        done = true;
+                        hard = true;
+                    }
+                }
             }
             if (done) {
                 // a root this close to the real axis (|arg| < 1e-5: below 0.1 Hz at any audio rate) is divided out as real
@@ -397,6 +426,7 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
                     M -= 2;
                 }
                 it = 0;
+                retried = false;
                 z = z_start;
                 active = (M >= 3);
             }
@@ -417,6 +447,12 @@ __global__ void __launch_bounds__(kRootsThreads) lpc_roots_pair_kernel(const Roo
         return;
     }
     if (!in_range) return;
+    if (Q.hard_mod > 0 && (f_raw % Q.hard_mod) == 0) hard = true;
+    if (hard && Q.hard_list) {
+        const unsigned idx = atomicAdd(Q.hard_count, 1u);
+        if (idx < (unsigned)Q.hard_cap) Q.hard_list[idx] = (int)f_raw;
+        if (Q.work) atomicAdd(Q.work + 4, 1ULL);
+    }
     // tail: what is left has degree 2, 1 or 0 (real coefficients)
     if (M == 2) {
         const TR q0 = c_s[tid], q1 = c_s[T + tid], q2 = c_s[2 * T + tid];

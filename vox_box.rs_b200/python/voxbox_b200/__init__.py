@@ -259,7 +259,7 @@ class Context:
         """Executed-work counters of the last profile_begin..profile_end window (vbx_profile_counters)."""
         out = (C.c_uint64 * 8)()
         self._check(self.lib.vbx_profile_counters(self.h, out, 8), "vbx_profile_counters")
-        return dict(roots_horner_steps=out[0], roots_rounds=out[1], refine_terms=out[2], refine_evals=out[3])
+        return dict(roots_horner_steps=out[0], roots_rounds=out[1], refine_terms=out[2], refine_evals=out[3], roots_fixup_frames=out[4])
 
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)
