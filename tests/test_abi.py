@@ -58,6 +58,93 @@ def test_rust_shim_declares_every_function():
     assert not [f for f in bound if f not in fns], "Rust extern block names a function the header does not declare"
 
 
+# The reference's public surface (src/*.rs of andrewcsmith/vox_box.rs; the line numbers are the reference's): every trait with
+# its methods, every public struct / enum / free function on the hot path.  The shim must spell them identically.
+REFERENCE_SURFACE = {
+    "traits": {
+        "Autocorrelate": ["autocorrelate_mut", "autocorrelate"],                          # periodic.rs:265-274
+        "Pitched": ["pitch"],                                                             # periodic.rs:356-358
+        "LagType": [],                                                                    # periodic.rs:232-234
+        "LPC": ["lpc_mut", "lpc", "lpc_praat_mut", "lpc_praat"],                          # spectrum.rs:50-55
+        "ToResonance": ["to_resonance"],                                                  # spectrum.rs:195-197
+        "EstimateFormants": ["estimate_formants"],                                        # spectrum.rs:216-219
+        "MFCC": ["mfcc"],                                                                 # spectrum.rs:371-373
+        "Polynomial": ["degree", "off_low", "laguerre", "find_roots_work_size", "find_roots", "find_roots_mut",
+                       "div_polynomial", "div_polynomial_mut"],                            # polynomial.rs:10-21
+        "RMS": ["rms"], "Amplitude": ["amplitude"], "MaxAmplitude": ["max_amplitude"],    # waves.rs:10-41
+        "Normalize": ["normalize_with_max", "normalize"], "Filter": ["preemphasis"],      # waves.rs:61-84
+    },
+    "types": ["Pitch", "PitchExtractor", "Interpolation", "HanningLag", "LPCSolver", "Resonance", "FormantExtractor",
+              "VoxBoxError", "VoxBoxResult"],
+    "functions": ["interpolate_sinc", "improve_extremum", "hz_to_mel", "mel_to_hz", "dct", "dct_mut", "find_formants",
+                  "find_formants_real_work_size", "find_formants_complex_work_size", "from_root", "with_context"],
+    "constants": ["MAX_RESONANCES", "MALE_FORMANT_ESTIMATES", "FEMALE_FORMANT_ESTIMATES"],
+    "signatures": [  # spelled as in the reference (whitespace-insensitive)
+        "fn autocorrelate_mut(&self, coeffs: &mut [T]);",
+        "fn lpc_mut(&self, n_coeffs: usize, ac: &mut [T], kc: &mut [T], tmp: &mut [T]);",
+        "fn lpc_praat_mut(&self, n_coeffs: usize, coeffs: &mut [T], work: &mut [T]) -> VoxBoxResult<()>;",
+        "fn lpc_praat(&self, n_coeffs: usize) -> VoxBoxResult<Vec<T>>;",
+        "fn pitch<W: LagType>(&self, sample_rate: T, threshold: T, local_peak: S, global_peak: S, min: T, max: T) -> Vec<Pitch<T>>;",
+        "fn to_resonance(&self, sample_rate: T) -> Vec<Resonance<T>>;",
+        "fn estimate_formants(&mut self, resonances: &[Resonance<T>]);",
+        "fn mfcc(&self, num_coeffs: usize, freq_bounds: (f64, f64), sample_rate: f64) -> Vec<T>;",
+        "fn laguerre(&self, z: Complex<T>) -> Complex<T>;",
+        "fn find_roots(&self) -> VoxBoxResult<Vec<Complex<T>>>;",
+        "fn div_polynomial(&mut self, other: Complex<T>) -> VoxBoxResult<Vec<Complex<T>>>;",
+        "fn div_polynomial_mut(&'a mut self, other: Complex<T>, rem: &'a mut [Complex<T>]) -> VoxBoxResult<()>;",
+        "fn normalize_with_max(&mut self, max: Option<S>);",
+        "fn preemphasis(&mut self, factor: f64) -> &mut Self;",
+        "pub fn new(num_formants: usize, resonances: I, starting_estimates: Vec<Resonance<T>>) -> Self",
+        "pub fn new(candidates: &'a [&'a [Pitch<T>]], voiced_unvoiced_cost: T, voicing_threshold: T) -> Self",
+        "pub fn interpolate_sinc<S: Elem>(y: &[S], offset: isize, nx: usize, x: S, max_depth: usize) -> f64",
+        "pub fn improve_extremum<S: Elem>(y: &[S], offset: isize, nx: usize, ixmid: f64, interp: Interpolation, is_max: bool) -> (f64, f64)",
+    ],
+}
+
+
+def test_rust_shim_mirrors_the_reference_trait_surface():
+    """north_star: "the existing Rust trait/function surface stays unchanged".  The shim (source only: no Rust toolchain here)
+    defines every trait of the reference with the same method names and signatures, implemented for slices / VecDeque, plus the
+    public types, free functions and constants of the path."""
+    rs = open(os.path.join(ROOT, "rust", "vox_box_b200", "src", "lib.rs")).read()
+    flat = re.sub(r"\s+", " ", rs)
+    for trait, methods in REFERENCE_SURFACE["traits"].items():
+        assert re.search(rf"pub trait {trait}\b", rs), f"trait {trait} missing"
+        m = re.search(rf"pub trait {trait}\b[^{{]*\{{(.*?)\n    \}}", rs, flags=re.S)
+        body = m.group(1) if m else ""
+        for meth in methods:
+            assert re.search(rf"fn {meth}\b", body), f"{trait}::{meth} missing from the trait definition"
+        if trait != "LagType":
+            assert re.search(rf"impl<[^>]*>\s+{trait}(<[^>]*>)?\s+for\s+(\[|VecDeque|S\b)", rs), f"no slice impl of {trait}"
+    assert re.search(r"impl<T: Elem> Autocorrelate<T> for VecDeque<T>", rs)   # periodic.rs:291-304
+    for t in REFERENCE_SURFACE["types"]:
+        assert re.search(rf"pub (struct|enum|type) {t}\b", rs), f"type {t} missing"
+    for f in REFERENCE_SURFACE["functions"]:
+        assert re.search(rf"pub fn {f}\b", rs), f"function {f} missing"
+    for c in REFERENCE_SURFACE["constants"]:
+        assert re.search(rf"pub const {c}\b", rs), f"constant {c} missing"
+    for sig in REFERENCE_SURFACE["signatures"]:
+        assert re.sub(r"\s+", " ", sig) in flat, f"signature not found verbatim: {sig}"
+    for mod in ("periodic", "spectrum", "polynomial", "waves", "error"):
+        assert re.search(rf"pub mod {mod}\b", rs), f"module {mod} missing"
+    # braces balance (a cheap stand-in for the compiler this image lacks)
+    code = re.sub(r"//[^\n]*", "", rs)
+    code = re.sub(r'"(\\.|[^"\\])*"', '""', code)
+    code = re.sub(r"'(\\.|[^'\\])'", "' '", code)
+    for a, b in ("{}", "()", "[]"):
+        assert code.count(a) == code.count(b), f"unbalanced {a}{b}: {code.count(a)} vs {code.count(b)}"
+
+
+def test_multi_partition_rule():
+    """vbx_multi_partition (host arithmetic, no GPU): contiguous, exhaustive, balanced to within one unit."""
+    for n, parts in ((4500, 8), (10, 3), (7, 8), (0, 4), (360000, 8)):
+        lo_hi = [vb.multi_partition(n, parts, p) for p in range(parts)]
+        assert lo_hi[0][0] == 0 and lo_hi[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(lo_hi, lo_hi[1:]))
+        sizes = [h - l for l, h in lo_hi]
+        assert max(sizes) - min(sizes) <= 1
+
+
 def test_formant_estimate_constants():  # lib.rs:27-28
     lib = vb.load_library()
     male = (C.c_double * 4).in_dll(lib, "VBX_MALE_FORMANT_ESTIMATES")
