@@ -940,6 +940,7 @@ static int lpc_to_resonances_impl(vbx_ctx* ctx, const void* lpc, int32_t lpc_dty
     Q.status_out = status_out; Q.n_frames = n_frames; Q.fs = sample_rate; Q.lpc_stride = lpc_stride;
     Q.lpc_has_one = lpc_has_leading_one ? 1 : 0; Q.lpc_f64 = (lpc_dtype == VBX_F64); Q.out_f64 = (out_dtype == VBX_F64);
     Q.R = res_slots; Q.strict_im = strict_im ? 1 : 0; Q.polish_steps = 2;
+    if (const char* e = getenv("VBX_ROOTS_POLISH")) Q.polish_steps = atoi(e);  // A/B runs
     Q.work = vbx_work_ptr(ctx);
     Q.in_J = in_J; Q.out_J = out_J; Q.out_j0 = out_j0;
     Q.hard_list = nullptr; Q.hard_count = nullptr; Q.hard_cap = 0; Q.hard_mod = 0; Q.frame_list = nullptr; Q.frame_count = nullptr;

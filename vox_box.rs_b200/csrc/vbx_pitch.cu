@@ -624,17 +624,20 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
 // 12 to 40), so in the lockstep version above a warp idles a finished slot until the slowest of its four is done.  Here
 // every slot draws its next candidate from the tile's sorted order (a shared-memory cursor) as soon as it finishes:
 // the warp stays in lockstep only over single evaluations of the interpolant.
+template <int LS, int TILE>  // lanes per slot: 8, 4 or 2 (4, 8 or 16 candidates per warp); TILE = work-list entries per tile
 __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P) {
+    static_assert(LS == 8 || LS == 4 || LS == 2, "an even term stride keeps (-1)^n a per-lane constant");
+    constexpr int SLOT_MASK = 32 - LS;  // lane & SLOT_MASK = the slot's first lane
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, l8 = lane & 7;
+    const int lane = threadIdx.x & 31, l8 = lane & (LS - 1);
     const long long total = (long long)*P.counter;
     const int N = P.n;
-    // A CTA takes tiles of kRefineTile consecutive work-list entries (about ten frames) and walks each tile in order of
+    // A CTA takes tiles of TILE consecutive work-list entries (about ten frames) and walks each tile in order of
     // the start abscissa, i.e. of the interpolation depth D: the four slots of a warp then run term loops of nearly the
     // same length (the list order — ascending lag inside a frame — leaves 19 % of the lanes of the term loop idle, a
     // sorted tile 3 %).  Results do not depend on the grouping: every slot's arithmetic is its own.
-    __shared__ float s_key[kRefineTile];
-    __shared__ unsigned short s_ord[kRefineTile];
+    __shared__ float s_key[TILE];
+    __shared__ unsigned short s_ord[TILE];
     __shared__ int s_next;
     __shared__ long long s_tile;
     const int offset = -P.ixmax - 1;
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
         s_next = 0;
     }
     __syncthreads();
-    const long long tile0 = s_tile * kRefineTile;
+    const long long tile0 = s_tile * TILE;
     if (tile0 >= total) {
         if (P.work && lane == 0) {  // warp-uniform counts, summed over lanes
             atomicAdd(P.work + 2, 32ULL * work_terms);
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
         }
         break;
     }
-    const int tcnt = (int)min((long long)kRefineTile, total - tile0);
+    const int tcnt = (int)min((long long)TILE, total - tile0);
     for (int i = threadIdx.x; i < tcnt; i += blockDim.x) s_key[i] = (float)P.list[tile0 + i].n;
     __syncthreads();
     for (int i = threadIdx.x; i < tcnt; i += blockDim.x) {
@@ -690,7 +693,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
             const bool want = !have && !dry;
             int qi = -1;
             if (want && l8 == 0) qi = atomicAdd(&s_next, 1);
-            qi = __shfl_sync(FULL, qi, lane & 24);
+            qi = __shfl_sync(FULL, qi, lane & SLOT_MASK);
             if (want) {
                 if (qi >= tcnt) {
                     dry = true;
@@ -750,11 +753,17 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
             // the three slot-uniform trigonometric values share ONE sincospi call: lane 0 of the slot takes πφ (→ sin πφ),
             // lane 1 takes 8δ_l, lane 2 takes 8δ_r; five shuffles hand the results to the other lanes of the slot
             double su, cu;
-            sincospi(l8 == 0 ? pl : (l8 == 1 ? 8.0 * inv_l : (l8 == 2 ? 8.0 * inv_r : 0.0)), &su, &cu);
-            const int sb = lane & 24;
+            sincospi(l8 == 0 ? pl : (l8 == 1 ? (double)LS * inv_l : (l8 == 2 ? (double)LS * inv_r : 0.0)), &su, &cu);
+            const int sb = lane & SLOT_MASK;
             const double s0 = __shfl_sync(FULL, su, sb);
             const double S8l = __shfl_sync(FULL, su, sb + 1), C8l = __shfl_sync(FULL, cu, sb + 1);
-            const double S8r = __shfl_sync(FULL, su, sb + 2), C8r = __shfl_sync(FULL, cu, sb + 2);
+            double S8r, C8r;
+            if (LS >= 4) {
+                S8r = __shfl_sync(FULL, su, sb + 2);
+                C8r = __shfl_sync(FULL, cu, sb + 2);
+            } else {  // two lanes per slot: the third slot-uniform angle gets its own call
+                sincospi((double)LS * inv_r, &S8r, &C8r);
+            }
             double sl, cl, sr, cr;
             double tl = pl + (double)l8, tr = pr + (double)l8;
             sincospi(tl * inv_l, &sl, &cl);
@@ -766,7 +775,7 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
             const double Kl = 2.0 * C8l, Kr = 2.0 * C8r, Cl = 1.0 - C8l, Cr = 1.0 - C8r;
             const int L = offset + nr, R = offset + nl;
             const int Dmax = __reduce_max_sync(FULL, D);
-            work_terms += (unsigned)((Dmax >= 0 ? Dmax : -1) + 8) >> 3;
+            work_terms += (unsigned)((Dmax >= 0 ? Dmax : -1) + LS) / LS;
             ++work_evals;
             double acc = 0.;
             // Left terms read y[L − n] (>= 0 because D <= L), right terms y[R + n]; beyond N the zero extension
@@ -777,19 +786,19 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
                 const int Dl = D, Dr = min(D, N - 1 - R);
                 const double* __restrict__ ql = y + (act ? L - l8 : 0);
                 const double* __restrict__ qr = y + (act ? R + l8 : 0);
-                for (int n = l8; n <= Dmax; n += 8) {
+                for (int n = l8; n <= Dmax; n += LS) {
                     const double yl = (n <= Dl) ? __ldg(ql) : 0.0;
                     const double yr = (n <= Dr) ? __ldg(qr) : 0.0;
-                    ql -= 8;
-                    qr += 8;
+                    ql -= LS;
+                    qr += LS;
                     const double num = fma(yl * hl, tr, (yr * hr) * tl);
                     acc = fma(num, rcp_pos(tl * tr), acc);
                     const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
                     hlp = hl; hl = nhl; hrp = hr; hr = nhr;
-                    tl += 8.0; tr += 8.0;
+                    tl += (double)LS; tr += (double)LS;
                 }
             } else {
-                for (int n = l8; n <= Dmax; n += 8) {
+                for (int n = l8; n <= Dmax; n += LS) {
                     const bool on = (n <= D);
                     int il = L - n;
                     il = il < 0 ? 0 : il;
@@ -802,13 +811,13 @@ __global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P
                     // advance: t += 8, Hann factors one recurrence step
                     const double nhl = fma(Kl, hl, Cl - hlp), nhr = fma(Kr, hr, Cr - hrp);
                     hlp = hl; hl = nhl; hrp = hr; hr = nhr;
-                    tl += 8.0; tr += 8.0;
+                    tl += (double)LS; tr += (double)LS;
                 }
             }
             acc *= sgn;
             acc += __shfl_xor_sync(FULL, acc, 1);
-            acc += __shfl_xor_sync(FULL, acc, 2);
-            acc += __shfl_xor_sync(FULL, acc, 4);
+            if (LS >= 4) acc += __shfl_xor_sync(FULL, acc, 2);
+            if (LS == 8) acc += __shfl_xor_sync(FULL, acc, 4);
             const double ft = special ? sval : acc * (s0 * (1.0 / kPi));
             // ---- Brent update (periodic.rs:121-186) ---------------------------------------------------------------------
             if (!done) {
@@ -1104,6 +1113,12 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     const char* rv = getenv("VBX_PITCH_REFINE");
     const bool refine_v0 = rv && rv[0] == 'v' && rv[1] == '0';  // the first (warp per candidate) version, kept for A/B runs
     const bool refine_v1 = rv && rv[0] == 'v' && rv[1] == '1';  // lockstep groups of four (no queue), kept for A/B runs
+    // Lanes per candidate slot of the queue-fed kernel.  Every evaluation of the interpolant pays ~300 instructions of setup (three
+    // sincospi, two reciprocals, the Brent update) whatever the slot width, so narrower slots — more candidates per warp —
+    // amortise it better: 8 lanes 5.70e6 frames/s on C4, 4 lanes 6.85e6, 2 lanes 7.06e6 (results identical: a slot's arithmetic
+    // is its own; 0 of 262 471 list positions off by > 0.1 Hz for each width).
+    int refine_lanes = 2;
+    if (const char* e = getenv("VBX_PITCH_REFINE_LANES")) refine_lanes = atoi(e) == 4 ? 4 : (atoi(e) == 8 ? 8 : 2);
     for (int64_t f0 = 0; f0 < fr->n_frames; f0 += slab) {
         P.frame0 = f0;
         P.n_frames = (fr->n_frames - f0 < slab) ? fr->n_frames - f0 : slab;
@@ -1125,15 +1140,27 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         } else if (refine_v1) {
             pitch_refine8_kernel<<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(P);
         } else {
-            static const int resident = [] {  // CTAs of the queue-fed kernel that fit one SM (computed once, thread-safely)
+            static const int resident8 = [] {  // CTAs of the queue-fed kernel that fit one SM (computed once, thread-safely)
                 int r = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pitch_refine8q_kernel, 128, 0) != cudaSuccess || r < 1) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pitch_refine8q_kernel<8, 256>, 128, 0) != cudaSuccess || r < 1) {
                     cudaGetLastError();
                     r = 4;
                 }
                 return r;
             }();
-            pitch_refine8q_kernel<<<ctx->sm_count * resident, 128, 0, ctx->stream>>>(P);
+            static const int resident4 = [] {
+                int r = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, pitch_refine8q_kernel<2, 256>, 128, 0) != cudaSuccess || r < 1) {
+                    cudaGetLastError();
+                    r = 4;
+                }
+                return r;
+            }();
+            // (tiles larger than 256 entries were measured slower for every slot width: a tile's ~10 lag-function rows stay
+            // in L1, 40 rows do not)
+            if (refine_lanes == 2) pitch_refine8q_kernel<2, 256><<<ctx->sm_count * resident4, 128, 0, ctx->stream>>>(P);
+            else if (refine_lanes == 4) pitch_refine8q_kernel<4, 256><<<ctx->sm_count * resident4, 128, 0, ctx->stream>>>(P);
+            else pitch_refine8q_kernel<8, 256><<<ctx->sm_count * resident8, 128, 0, ctx->stream>>>(P);
         }
         VBX_CHECK_LAUNCH(ctx, refine_v0 ? "pitch_refine_kernel" : (refine_v1 ? "pitch_refine8_kernel" : "pitch_refine8q_kernel"));
         pitch_finalize_kernel<<<(unsigned)((P.n_frames + 3) / 4), 128, 0, ctx->stream>>>(P, cand_out, max_cand, n_cand_out,
