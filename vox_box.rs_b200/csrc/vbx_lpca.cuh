@@ -79,7 +79,6 @@ template <int L, typename TIn>
 __global__ void __launch_bounds__(256) lpc_fuseda_kernel(const LpcParams P, const LpcaExtra X) {
     static_assert(L >= 2 && L <= kLpcaMaxLags, "the seed fix-up needs a + lag <= 15");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_nonfinite;
     double* s_tab = reinterpret_cast<double*>(smem_raw);                   // [2][wt]
     float* s_span = reinterpret_cast<float*>(s_tab + 2 * X.wt);             // aligned span (16-byte aligned: wt is even)
     double* s_out = reinterpret_cast<double*>(s_span);                     // staging, reuses the span after a barrier
@@ -96,7 +95,6 @@ __global__ void __launch_bounds__(256) lpc_fuseda_kernel(const LpcParams P, cons
     const int mis = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(TIn)) & (A - 1));
     const TIn* __restrict__ src_al = src - mis;                            // 16-byte aligned
 
-    if (tid == 0) s_nonfinite = 0;
     // ---- stage the window rows and the span (word s of the span = sample src_al[s]; zeros outside the real samples) --------
     {
         const double2* t2 = reinterpret_cast<const double2*>(X.tabs);
@@ -169,9 +167,7 @@ __global__ void __launch_bounds__(256) lpc_fuseda_kernel(const LpcParams P, cons
             }
         }
     }
-    if (bad) s_nonfinite = 1;
-    __syncthreads();
-    const bool guard = (s_nonfinite != 0);
+    const bool guard = __syncthreads_or(bad) != 0;  // the staging barrier also tells every thread whether anybody saw an Inf / NaN
 
     // ---- per-lane partial autocorrelation over the lane's chunks ----------------------------------------------------------
     const int q = tid / G, g = tid - q * G;   // part, frame

@@ -126,7 +126,8 @@ __device__ __forceinline__ void pitch_lag_post(const PitchParams& P, unsigned ch
             pos = atomicAdd(P.counter, (unsigned long long)count);
             P.range[f_first + qf] = make_int2((int)pos, count);
         }
-        const int start = (int)__shfl_sync(FULL, pos, 0);  // also orders the staging writes before the reads below
+        const int start = (int)__shfl_sync(FULL, pos, 0);
+        __syncwarp();  // the staging writes above are read by other lanes below
         for (int i = lane; i < count; i += 32) {
             PitchCand e;
             e.frame = (int)(f_first + qf);

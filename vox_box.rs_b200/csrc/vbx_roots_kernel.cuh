@@ -67,22 +67,56 @@ struct RootsParams {
 // ---------------------------------------------------------------------------------------------
 constexpr int kRootsThreads = 128;
 
+// approximate reciprocal / principal complex square root for the fp32 fast path (the f64 instantiations fall back to the
+// exact operations; they are never used by FAST code).  One MUFU each, flush-to-zero: the callers keep the arguments in
+// the normal range.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ vcx<float> csqrt_fast(vcx<float> a) {
+    const float n2 = a.re * a.re + a.im * a.im;
+    // |a|² outside the comfortable fp32 range (an iterate that sits on a root to the last bit makes a1 / a0 huge), zero or
+    // NaN: the overflow-safe hypot form
+    if (!(n2 >= 1.0e-30f && n2 <= 1.0e30f)) return csqrt_principal(a);
+    const float r = n2 * fast_rsqrt(n2);                  // |a|
+    // the larger of sqrt((r ± re)/2) is computed directly (no cancellation), the other follows from re·im = a.im / 2
+    const float big = 0.5f * (r + fabsf(a.re));
+    const float rs = fast_rsqrt(big);
+    const float t = big * rs;                             // sqrt(big)
+    const float small = 0.5f * fabsf(a.im) * rs;          // |a.im| / (2·sqrt(big))
+    const bool neg_im = (a.im < 0.f) || (a.im == 0.f && signbit(a.im));
+    if (a.re >= 0.f) return cmk<float>(t, neg_im ? -small : small);
+    return cmk<float>(small, neg_im ? -t : t);
+}
+__device__ __forceinline__ vcx<double> csqrt_fast(vcx<double> a) { return csqrt_principal(a); }
+
 // Laguerre update (polynomial.rs:48-69) from the Horner triple (a0, a1, a2) = (P, P', P''/2) at z: returns the step n/cc.
 // FAST (fp32 path, polished in fp64 afterwards): one reciprocal per complex division instead of two IEEE divisions and
 // squared magnitudes for the |cc1| > |cc2| choice; the fp64 path keeps the reference's operations one for one.
 template <typename TR, bool FAST>
 __device__ __forceinline__ vcx<TR> laguerre_step(vcx<TR> a0, vcx<TR> a1, vcx<TR> a2, TR nn, TR nref) {
     if (FAST) {
-        const TR inv0 = (TR)1 / cnorm_sqr(a0);
+        // The fp32 iterate is self-correcting and polished in fp64 afterwards, so this path uses the hardware's approximate
+        // reciprocal / reciprocal square root (1-2 ulp, one MUFU each) instead of IEEE divisions, hypotf and sqrtf: the step
+        // changes in its last bits, the root it converges to does not (~60 instructions fewer per round).
+        const TR inv0 = fast_rcp(cnorm_sqr(a0));
         const vcx<TR> ca = cmk<TR>(-(a1.re * a0.re + a1.im * a0.im) * inv0, -(a1.im * a0.re - a1.re * a0.im) * inv0);
         const vcx<TR> ca2 = cmul(ca, ca);
         const vcx<TR> t2 = cmk<TR>((TR)2 * (a2.re * a0.re + a2.im * a0.im) * inv0, (TR)2 * (a2.im * a0.re - a2.re * a0.im) * inv0);
         const vcx<TR> cb = csub(ca2, t2);
-        const vcx<TR> c1 = csqrt_principal(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
+        const vcx<TR> c1 = csqrt_fast(cmk<TR>(nn * cb.re - ca2.re, nn * cb.im - ca2.im));
         const vcx<TR> cc1 = cadd(ca, c1), cc2 = csub(ca, c1);
         const TR n1 = cnorm_sqr(cc1), n2 = cnorm_sqr(cc2);
         const vcx<TR> den = (n1 > n2) ? cc1 : cc2;
-        const TR invd = nref / ((n1 > n2) ? n1 : n2);
+        const TR invd = nref * fast_rcp((n1 > n2) ? n1 : n2);
         return cmk<TR>(den.re * invd, -den.im * invd);  // n / den = n·conj(den)/|den|²
     } else {
         const vcx<TR> ca = cdiv(cneg(a1), a0);
