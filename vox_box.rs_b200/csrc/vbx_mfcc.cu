@@ -59,6 +59,7 @@ template <typename R> __device__ __forceinline__ cxt<R> mulnegi(cxt<R> a) { retu
 
 // one radix-R Stockham butterfly: inputs src[j + t·T], twiddled by W_{Ls·R}^{k·t}, outputs dst[(j−k)·R + k + u·Ls]
 #include "vbx_mfcc_fast.cuh"  // inside the anonymous namespace: uses cxt<> and the complex helpers above
+#include "vbx_mfcc_lane5.cuh" // five lanes per frame for 400-sample frames (uses mfcc_fast::bfly)
 
 template <int R, typename TR>
 __device__ __forceinline__ void butterfly(const cxt<TR>* __restrict__ src, cxt<TR>* __restrict__ dst, const cxt<TR>* __restrict__ tw,
@@ -268,6 +269,8 @@ struct MfccTables {
     double *wu = nullptr, *wd = nullptr, *dct = nullptr;
     int* bins = nullptr;
     int4* items = nullptr;  // [num_coeffs + 1] intervals between bin edges {j, first bin, end bin, 0}, longest first
+    mfcc_lane5::Tables* l5 = nullptr;  // mfcc_lane5_kernel's tables (400-sample frames only)
+    int l5_prog_len = 0, l5_pw_len = 0;
     int kmin = 0, kmax = 0;
     int bad = 0;  // a bin the reference would panic on
 };
@@ -346,6 +349,14 @@ int get_tables(vbx_ctx* ctx, int n, int num_coeffs, int n_keep, double f_lo, dou
         std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return a.z - a.y > b.z - b.y; });
     }
     if ((st = up(items.data(), items.size() * sizeof(int4), (void**)&t.items)) != VBX_OK) return st;
+    if (!t.bad && n == mfcc_lane5::N && num_coeffs + 1 <= mfcc_lane5::kMaxItems && t.kmax <= n) {
+        std::vector<mfcc_lane5::Tables> l5(1);
+        if (mfcc_lane5::build_tables(l5[0], bins.data(), num_coeffs, wu.data(), wd.data())) {
+            t.l5_prog_len = l5[0].prog_len;
+            t.l5_pw_len = l5[0].pw_len;
+            if ((st = up(l5.data(), sizeof(mfcc_lane5::Tables), (void**)&t.l5)) != VBX_OK) return st;
+        }
+    }
     cache.push_back(t);
     *out = &cache.back();
     return VBX_OK;
@@ -455,6 +466,28 @@ int launch_mfcc(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, 
     bool f32 = ctx->mfcc_fft_f32;
     if (const char* e = getenv("VBX_MFCC_FFT")) f32 = (e[0] == 'f' && e[1] == '3');
     // (f64 samples — single windowed frames from the Rust shim's trait calls — take the generic kernel)
+    // 400-sample frames, fp64 transform, sample pairs loadable as one word: five lanes per frame (vbx_mfcc_lane5.cuh)
+    if constexpr (!std::is_same<TIn, double>::value) {
+        const char* e5 = getenv("VBX_MFCC_LANE5");
+        const size_t pair_bytes = 2 * sizeof(TIn);
+        const bool aligned = (reinterpret_cast<uintptr_t>(P.base) % pair_bytes) == 0 && (P.stride % 2) == 0 && (P.seg_stride % 2) == 0;
+        const mfcc_lane5::Smem L(num_coeffs, n_keep, t->l5_prog_len, t->l5_pw_len);
+        if (t->l5 && !f32 && aligned && !(e5 && e5[0] == '0') && !getenv("VBX_MFCC_GENERIC") && L.total <= ctx->smem_optin) {
+            mfcc_lane5::Params Q;
+            Q.base = P.base; Q.win = P.win; Q.dct = P.dct; Q.t = t->l5; Q.prog_len = t->l5_prog_len; Q.pw_len = t->l5_pw_len;
+            Q.out = P.out; Q.energies_out = P.energies_out;
+            Q.n_frames = P.n_frames; Q.stride = P.stride; Q.seg_frames = P.seg_frames; Q.seg_stride = P.seg_stride;
+            Q.num_coeffs = num_coeffs; Q.n_keep = n_keep; Q.out_f64 = P.out_f64;
+            auto kern = mfcc_lane5::mfcc_lane5_kernel<TIn>;
+            VBX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            const int64_t n_groups = (P.n_frames + mfcc_lane5::FW - 1) / mfcc_lane5::FW;
+            int64_t grid = (n_groups + mfcc_lane5::PAIRS - 1) / mfcc_lane5::PAIRS;
+            if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent: one CTA per SM, warps loop over groups of six frames
+            kern<<<(unsigned)grid, mfcc_lane5::WARPS * 32, L.total, ctx->stream>>>(Q);
+            VBX_CHECK_LAUNCH(ctx, "mfcc_lane5_kernel");
+            return VBX_OK;
+        }
+    }
     if constexpr (!std::is_same<TIn, double>::value)
     if (P.mode == 0 && !getenv("VBX_MFCC_GENERIC") && P.kmax <= n && num_coeffs <= 128 && n_keep * num_coeffs <= 2048) {
         mfcc_fast::FastParams Q;
@@ -501,7 +534,7 @@ int mfcc_check(vbx_ctx* ctx, const vbx_frames* fr, int num_coeffs, int n_keep, d
 void vbx_mfcc_cache_free(vbx_ctx* ctx) {
     if (!ctx->mfcc_cache) return;
     for (auto& t : ctx->mfcc_cache->tables) {
-        cudaFree(t.tw); cudaFree(t.wu); cudaFree(t.wd); cudaFree(t.dct); cudaFree(t.bins); cudaFree(t.items);
+        cudaFree(t.tw); cudaFree(t.wu); cudaFree(t.wd); cudaFree(t.dct); cudaFree(t.bins); cudaFree(t.items); cudaFree(t.l5);
     }
     delete ctx->mfcc_cache;
     ctx->mfcc_cache = nullptr;
