@@ -181,3 +181,63 @@ def test_mfcc_fast_kernels_every_specialised_length(oracle, N, monkeypatch):
     finally:
         c.mfcc_set_fft_precision(vb.F64)
     assert np.median(normwise(out32, ref)) < 1e-6
+
+
+@pytest.mark.parametrize("M,keep,lo,hi,window", [
+    (40, 13, 133.0, 6855.0, vb.WINDOW_HANN_SYMMETRIC),   # C5: num_coeffs divisible by 4 → the folded DCT
+    (26, 13, 100.0, 7000.0, vb.WINDOW_HANN_PERIODIC),    # plain DCT loop
+    (13, 13, 100.0, 8000.0, vb.WINDOW_NONE),             # odd num_coeffs (padded energy row); bins up to the Nyquist slot
+    (44, 20, 20.0, 7900.0, vb.WINDOW_HANN_SYMMETRIC),    # empty low-frequency intervals, bins folded above N/2, two rows per twin
+])
+@pytest.mark.parametrize("dtype", ["f32", "i16"])
+def test_mfcc_lane5_kernel(oracle, monkeypatch, M, keep, lo, hi, window, dtype):
+    """mfcc_lane5_kernel (400-sample frames: five lanes per frame, twin warps per group of six frames): several utterances as
+    segments, a frame count that leaves a ragged last group, energies, f32 and PCM input, f64 and f32 output — against the
+    oracle, against mfcc_warp_kernel, and the kernel that ran is checked by name."""
+    fs, N, hop, U = 16000, 400, 160, 5
+    ns = fs + 48   # even: every frame starts on a sample pair
+    audio = np.stack([synth.utterance(300 + u, fs, seconds=ns / fs)[:ns] for u in range(U)])
+    c = ctx()
+    J = c.n_frames_of(ns, N, hop)
+    F = U * J
+    assert F % 6 != 0   # the last group of six frames is ragged
+    if dtype == "i16":
+        pcm = np.round(audio * 32767.0).astype(np.int16)
+        d = c.to_device(pcm)
+        host = (pcm.astype(np.float64) / 32767.0).astype(np.float32)   # the oracle's input type: 6e-8 away from the PCM path's samples
+        fr = c.frames(d.ptr, F, N, hop, window, dtype=vb.I16, frames_per_segment=J, segment_stride=ns)
+    else:
+        d = c.to_device(audio.astype(np.float32))
+        host = audio.astype(np.float32)
+        fr = c.frames(d.ptr, F, N, hop, window, frames_per_segment=J, segment_stride=ns)
+    c.profile_begin()
+    out, en = c.mfcc(fr, M, lo, hi, float(fs), n_keep=keep, want_energies=True)
+    assert "mfcc_lane5_kernel" in c.profile_end()
+    out, en = out.to_host(), en.to_host()
+    monkeypatch.setenv("VBX_MFCC_LANE5", "0")
+    c.profile_begin()
+    old, old_en = c.mfcc(fr, M, lo, hi, float(fs), n_keep=keep, want_energies=True)
+    assert "mfcc_warp_kernel" in c.profile_end()
+    monkeypatch.delenv("VBX_MFCC_LANE5")
+    assert normwise(out, old.to_host()).max() < 1e-12 and normwise(en, old_en.to_host()).max() < 1e-12
+    win = {vb.WINDOW_HANN_SYMMETRIC: oracle.WIN_HANN_SYMMETRIC, vb.WINDOW_HANN_PERIODIC: oracle.WIN_HANN_PERIODIC,
+           vb.WINDOW_NONE: oracle.WIN_NONE}[window]
+    ref = np.concatenate([oracle.batch_mfcc(host[u], J, N, hop, win, M, lo, hi, float(fs), n_keep=keep, n_threads=0) for u in range(U)])
+    assert normwise(out, ref).max() < (1e-9 if dtype == "f32" else TOL_MFCC)
+    out32 = c.mfcc(fr, M, lo, hi, float(fs), n_keep=keep, out_dtype=vb.F32).to_host()
+    assert out32.dtype == np.float32 and normwise(out32, out).max() < 1e-6
+
+
+def test_mfcc_lane5_kernel_falls_back_on_odd_offsets(oracle):
+    """Frames that do not start on a sample pair (odd hop, odd base offset) cannot use the paired loads: the warp kernel runs."""
+    fs, N = 16000, 400
+    audio = synth.utterance(77, fs, seconds=1.0)
+    c = ctx()
+    d = c.to_device(audio)
+    for base_off, hop in ((1, 160), (0, 161)):
+        F = c.n_frames_of(audio.size - base_off, N, hop)
+        c.profile_begin()
+        out = c.mfcc(c.frames(d.ptr + 4 * base_off, F, N, hop, vb.WINDOW_HANN_SYMMETRIC), 40, 133.0, 6855.0, float(fs), n_keep=13).to_host()
+        assert "mfcc_warp_kernel" in c.profile_end()
+        ref = oracle.batch_mfcc(audio[base_off:], F, N, hop, oracle.WIN_HANN_SYMMETRIC, 40, 133.0, 6855.0, float(fs), n_keep=13, n_threads=0)
+        assert normwise(out, ref).max() < 1e-9
