@@ -84,6 +84,72 @@ def pair_roots(a_asc, z0, eps):
     return roots, work, capped
 
 
+def pair_roots_real(a_asc, z0, eps):
+    """The same solver with the polynomial evaluated in REAL arithmetic: P, P', P''/2 at z from three chained synthetic
+    divisions by x^2 - 2 Re(z) x + |z|^2 (6 real multiply-adds per coefficient instead of complex Horner's 12), and the
+    deflation done by one more sweep at the converged root whose quotient (the first division's b) becomes the working
+    polynomial.  Returns (roots, coefficient steps incl. the deflation sweeps, capped solves)."""
+    P = len(a_asc) - 1
+    c = np.array(a_asc, dtype=f32)
+    M, work, capped, roots = P, 0, 0, []
+    nn, nref = f32((P - 1) * P), f32(P)
+
+    def sweep(c, M, p, q):
+        b = np.zeros(M + 3, dtype=f32)
+        d = np.zeros(M + 3, dtype=f32)
+        e = np.zeros(M + 3, dtype=f32)
+        for k in range(M, -1, -1):
+            b[k] = f32(f32(c[k] + f32(p * b[k + 1])) - f32(q * b[k + 2])) if False else f32(np.float32(c[k]) + np.float32(p) * b[k + 1] - np.float32(q) * b[k + 2])
+            if k >= 2:
+                d[k - 2] = f32(b[k] + p * d[k - 1] - q * d[k])
+            if k >= 4:
+                e[k - 4] = f32(d[k - 2] + p * e[k - 3] - q * e[k - 2])
+        return b, d, e
+
+    while M >= 3:
+        z, conv = c64(z0), False
+        for _ in range(20):
+            x0, y0 = f32(z.real), f32(z.imag)
+            p, q = f32(2 * x0), f32(x0 * x0 + y0 * y0)
+            b, d, e = sweep(c, M, p, q)
+            work += M
+            a0 = c64(complex(b[0] - x0 * b[1], y0 * b[1]))
+            Qz = c64(complex(d[0] - x0 * d[1], y0 * d[1]))
+            Sz = c64(complex(e[0] - x0 * e[1], y0 * e[1]))
+            a1 = c64(2j * y0 * Qz + b[1])
+            a2 = c64(Qz - 4 * y0 * y0 * Sz + 2j * y0 * d[1])
+            if abs(a0) ** 2 <= 1e-32:
+                conv = True
+                break
+            st = laguerre_step(a0, a1, a2, nn, nref)
+            z = c64(z + st)
+            if abs(st) ** 2 <= eps ** 2 * abs(z) ** 2:
+                conv = True
+                break
+        capped += 0 if conv else 1
+        work += M  # the deflation sweep
+        if abs(z.imag) <= 1e-5 * abs(z.real):
+            roots.append(complex(z.real, 0))
+            b, _, _ = sweep(c, M, f32(z.real), f32(0))
+            c = np.concatenate([b[1:M + 1], np.zeros(1, dtype=f32)]).astype(f32)
+            M -= 1
+        else:
+            roots += [complex(z.real, abs(z.imag)), complex(z.real, -abs(z.imag))]
+            x0, y0 = f32(z.real), f32(z.imag)
+            b, _, _ = sweep(c, M, f32(2 * x0), f32(x0 * x0 + y0 * y0))
+            c = np.concatenate([b[2:M + 1], np.zeros(2, dtype=f32)]).astype(f32)
+            M -= 2
+    if M == 2:
+        q0, q1, q2 = c[0], c[1], c[2]
+        disc, inv = q1 * q1 - 4 * q2 * q0, 1 / (2 * q2)
+        sq = np.sqrt(abs(disc))
+        roots += ([complex(-q1 * inv, abs(sq * inv)), complex(-q1 * inv, -abs(sq * inv))] if disc < 0
+                  else [complex((-q1 + sq) * inv, 0), complex((-q1 - sq) * inv, 0)])
+    elif M == 1:
+        roots.append(complex(-c[0] / c[1], 0))
+    return roots, work, capped
+
+
 def resonances(roots, a_desc, fs, polish):
     out = []
     for z in roots:
@@ -116,12 +182,15 @@ def main():
             lpcs += [ac[f] for f in range(F)]
         truth = [resonances([complex(z) for z in np.roots(a)], a, fs, 0) for a in lpcs]
         print(f"fs = {fs}: {len(lpcs)} LPC-12 polynomials")
+        real = len(sys.argv) > 2 and sys.argv[2] == "real"
+        if real:
+            print("  (real-arithmetic evaluation: three chained synthetic divisions + a deflation sweep per root)")
         for z0, eps in ((-2 - 2j, 3e-7), (0 + 1j, 3e-7), (0.7 + 0.7j, 3e-7), (0.3 + 0.9j, 3e-7), (0.3 + 0.9j, 1e-5),
                         (0.3 + 0.9j, 1e-4), (0.3 + 0.9j, 1e-3)):
             work = capped = mism = 0
             worst = 0.0
             for a, ref in zip(lpcs, truth):
-                roots, w, cp = pair_roots(a[::-1].copy(), z0, eps)
+                roots, w, cp = (pair_roots_real if real else pair_roots)(a[::-1].copy(), z0, eps)
                 work += w
                 capped += cp
                 got = resonances(roots, a, fs, 2)
