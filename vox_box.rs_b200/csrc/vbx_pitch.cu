@@ -625,8 +625,11 @@ __global__ void __launch_bounds__(128) pitch_refine8_kernel(const PitchParams P)
 // 12 to 40), so in the lockstep version above a warp idles a finished slot until the slowest of its four is done.  Here
 // every slot draws its next candidate from the tile's sorted order (a shared-memory cursor) as soon as it finishes:
 // the warp stays in lockstep only over single evaluations of the interpolant.
+#ifndef VBX_REFINE_MINB
+#define VBX_REFINE_MINB 1
+#endif
 template <int LS, int TILE>  // lanes per slot: 8, 4 or 2 (4, 8 or 16 candidates per warp); TILE = work-list entries per tile
-__global__ void __launch_bounds__(128) pitch_refine8q_kernel(const PitchParams P) {
+__global__ void __launch_bounds__(128, VBX_REFINE_MINB) pitch_refine8q_kernel(const PitchParams P) {
     static_assert(LS == 8 || LS == 4 || LS == 2, "an even term stride keeps (-1)^n a per-lane constant");
     constexpr int SLOT_MASK = 32 - LS;  // lane & SLOT_MASK = the slot's first lane
     const unsigned FULL = 0xffffffffu;
@@ -1088,7 +1091,11 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
     if constexpr (!std::is_same<TIn, double>::value) {
         if (lag_f32) VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (!lag_f32) VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag64_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool lag_small = threads <= 160;
+    if (!lag_f32) {
+        if (lag_small) VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag64_kernel<TIn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else VBX_CUDA(ctx, cudaFuncSetAttribute(pitch_lag64_kernel<TIn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
 
     // scratch per frame: y [N] f64 + worst-case candidate capacity (every other lag below N/2 a maximum)
     const int cap = P.ixmax / 2 + 1;
@@ -1129,7 +1136,10 @@ int launch_pitch(vbx_ctx* ctx, const vbx_frames* fr, double fs, double threshold
         if constexpr (!std::is_same<TIn, double>::value) {
             if (lag_f32) pitch_lag_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
         }
-        if (!lag_f32) pitch_lag64_kernel<TIn><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+        if (!lag_f32) {
+            if (lag_small) pitch_lag64_kernel<TIn, true><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+            else pitch_lag64_kernel<TIn, false><<<(unsigned)grid, threads, smem, ctx->stream>>>(P);
+        }
         VBX_CHECK_LAUNCH(ctx, lag_f32 ? "pitch_lag_kernel" : "pitch_lag64_kernel");
         if (lag_out) {  // vbx_pitch_lag_function: hand the lag function out and stop here
             VBX_CUDA(ctx, cudaMemcpyAsync(lag_out + (size_t)f0 * n, P.y, (size_t)P.n_frames * n * sizeof(double), cudaMemcpyDeviceToDevice,

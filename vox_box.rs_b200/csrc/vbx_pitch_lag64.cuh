@@ -39,8 +39,9 @@ __device__ __forceinline__ void lag_step64(double (&acc)[16], const D8& A, const
     }
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(256) pitch_lag64_kernel(const PitchParams P) {
+// SMALL: CTAs of at most 160 threads (every frame length up to 5 120 samples) — four of them per SM (96 registers)
+template <typename TIn, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 160 : 256, SMALL ? 4 : 1) pitch_lag64_kernel(const PitchParams P) {
     extern __shared__ __align__(16) double xd_all[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int n = P.n;
