@@ -1166,10 +1166,20 @@ int vbx_find_formants(vbx_ctx* ctx, const vbx_frames* frames, double sample_rate
     if (const char* e = getenv("VBX_FORMANT_SIDE"))
         if (e[0] == '0') side_stream = ctx->stream;
     // chunk boundaries on multiples of 32 frames (the LPC kernels' tile): only an utterance's last tile is partial
+    // The last chunk's tracker is the only one nobody overlaps, so the last two chunks are shorter than the others (3/4 and
+    // 1/2 of a share): the exposed tail shrinks with the chunk, the chunks before it grow by 10 %.
+    const bool taper = (K >= 4) && !getenv("VBX_FORMANT_UNIFORM");
     auto chunk_begin = [&](int c) -> int64_t {
         if (c <= 0) return 0;
         if (c >= K) return J;
-        int64_t j = (J * c) / K;
+        int64_t j;
+        if (taper) {
+            const double total = (double)K - 0.75;   // K − 2 full shares + 0.75 + 0.5
+            const double cum = (c <= K - 2) ? (double)c : (double)(K - 2) + 0.75;
+            j = (int64_t)((double)J * cum / total);
+        } else {
+            j = (J * c) / K;
+        }
         if (J >= 64 * (int64_t)K) j = ((j + 16) / 32) * 32;
         return j < J ? j : J;
     };
