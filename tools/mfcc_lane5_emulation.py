@@ -9,9 +9,20 @@ MC, N = 200, 400
 W = lambda n, e: np.exp(-2j * np.pi * e / n)
 
 
+def col(b, kB):
+    """column of butterfly (b, kB)'s inputs inside block b: blocks 5..7 are mirrored, so the partner's loads are base + s too"""
+    return 4 - kB if b >= 5 else kB
+
+
+def slot(k):
+    """where the spectrum's bin k lives after pass C ("kA-major": consecutive bins are 25 slots = one bank group apart)"""
+    return MC if k == MC else 25 * (k % 8) + k // 8
+
+
 def transform(x):
+    """the kernel's data flow on one frame: returns (X in natural order read through slot(), per-slot write counts)"""
     z = x[0::2] + 1j * x[1::2]
-    buf = np.zeros(MC + 1, complex)
+    buf = np.zeros(MC + 5, complex)
     # pass A: radix 8 over t, butterfly n1 = s + 5 i, output u at 25 u + n1, twiddle W200^(n1 u)
     for s in range(5):
         for i in range(5):
@@ -20,20 +31,19 @@ def transform(x):
             Y = np.array([sum(v[t] * W(8, t * u) for t in range(8)) for u in range(8)])
             for u in range(8):
                 buf[25 * u + n1] = Y[u] * W(200, n1 * u)
-    # pass B: radix 5 inside every 25-block b, butterfly j = s; output kB stored TRANSPOSED at 25 b + 5 s + kB
+    # pass B: radix 5 inside every 25-block b, butterfly j = s; output kB stored TRANSPOSED at 25 b + 5 s + col(b, kB)
     nb = buf.copy()
     for b in range(8):
         for s in range(5):
             v = np.array([buf[25 * b + s + 5 * t] for t in range(5)])
             for kB in range(5):
-                nb[25 * b + 5 * s + kB] = W(25, s * kB) * sum(v[t] * W(5, t * kB) for t in range(5))
+                nb[25 * b + 5 * s + col(b, kB)] = W(25, s * kB) * sum(v[t] * W(5, t * kB) for t in range(5))
     buf = nb
-    # pass C + untangle.  butterfly (kA, kB): inputs buf[25 kA + 5 j + kB], output kC = Z[kA + 8 kB + 40 kC]
+    # pass C + untangle.  butterfly (kA, kB): inputs buf[25 kA + 5 j + col], output kC = Z[kA + 8 kB + 40 kC]
     def bf(kA, kB):
-        v = np.array([buf[25 * kA + 5 * j + kB] for j in range(5)])
+        v = np.array([buf[25 * kA + 5 * j + col(kA, kB)] for j in range(5)])
         return np.array([sum(v[j] * W(5, j * kC) for j in range(5)) for kC in range(5)])
-    slot = lambda kA, kB, kC: 25 * kA + 5 * kC + kB   # where X_k lands (the slot butterfly (kA, kB) read input j = kC from)
-    out = np.zeros(MC + 1, complex)
+    out = np.zeros(MC + 5, complex)
     def pair(za, zb, k):
         E = 0.5 * (za + np.conj(zb)); O = 0.5 * (za - np.conj(zb)); T = W(N, k) * O
         return E - 1j * T, np.conj(E) - 1j * np.conj(T)
@@ -42,33 +52,30 @@ def transform(x):
         for kA in (1, 2, 3):
             units.append((s, (kA, s), (8 - kA, 4 - s), "regular"))
         units.append((s, [(4, 0), (4, 1), (0, 1), (0, 2), (0, 0)][s], [(4, 4), (4, 3), (0, 4), (0, 3), (4, 2)][s], "singles" if s == 4 else "regular"))
-    seen = np.zeros(MC + 1, int)
+    seen = np.zeros(MC + 5, int)
     for s, c, cp, kind in units:
         A, B = bf(*c), bf(*cp)
         k_of = lambda cc, kC: cc[0] + 8 * cc[1] + 40 * kC
         if kind == "regular":
-            ops = [(A[i], B[4 - i], k_of(c, i), slot(*c, i), slot(*cp, 4 - i)) for i in range(5)]
+            ops = [(A[i], B[4 - i], k_of(c, i), k_of(cp, 4 - i)) for i in range(5)]
         else:  # c = (0,0): Z[40 kC]; cp = (4,2): Z[20 + 40 kC]
-            ops = [(A[0], A[0], 0, slot(*c, 0), MC), (A[1], A[4], 40, slot(*c, 1), slot(*c, 4)), (A[2], A[3], 80, slot(*c, 2), slot(*c, 3)),
-                   (B[0], B[4], 20, slot(*cp, 0), slot(*cp, 4)), (B[1], B[3], 60, slot(*cp, 1), slot(*cp, 3)), (B[2], B[2], 100, slot(*cp, 2), slot(*cp, 2))]
-        for za, zb, k, sa, sb in ops:
+            ops = [(A[0], A[0], 0, MC), (A[1], A[4], 40, 160), (A[2], A[3], 80, 120), (B[0], B[4], 20, 180), (B[1], B[3], 60, 140), (B[2], B[2], 100, 100)]
+        for za, zb, k, k2 in ops:
+            assert k + k2 == MC
             xa, xb = pair(za, zb, k)
-            out[sa] = xa; out[sb] = xb
-            seen[sa] += 1; seen[sb] += 1
-    # natural-order view through the slot map: bin k = kA + 8 kB + 40 kC at 25 kA + 5 kC + kB, Nyquist at MC
-    X = np.zeros(MC + 1, complex)
-    for k in range(MC):
-        kA, r = k % 8, k // 8
-        X[k] = out[25 * kA + 5 * (r // 5) + (r % 5)]
-    X[MC] = out[MC]
+            out[slot(k)] = xa; out[slot(k2)] = xb
+            seen[slot(k)] += 1; seen[slot(k2)] += 1
+    X = np.array([out[slot(k)] for k in range(MC + 1)])
     return X, seen
 
 
-rng = np.random.default_rng(1)
-x = rng.standard_normal(N)
-X, seen = transform(x)
-ref = np.fft.rfft(x)
-print("max |X - rfft|:", np.max(np.abs(X - ref)), " every slot written:", bool(np.all(seen >= 1)), " written twice:", np.flatnonzero(seen > 1).tolist())
+def check(seed=1):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(N)
+    X, seen = transform(x)
+    ref = np.fft.rfft(x)
+    twice = np.flatnonzero(seen > 1).tolist()
+    return float(np.max(np.abs(X - ref))), bool(np.all(seen[:MC + 1] >= 1)), twice
 
 
 # ---- shared-memory wavefronts of a warp-wide 16-byte access: lane = 5 q + s (30 lanes), element index q FS + f(s) ------------
@@ -85,6 +92,11 @@ def wavefronts(FS, f):
     return tot
 
 
-pats = {"+s": lambda s: s, "-s": lambda s: 100 - s, "+5s": lambda s: 5 * s, "-5s": lambda s: 100 - 5 * s}
-for FS in range(200, 216):
-    print(FS, {k: wavefronts(FS, f) for k, f in pats.items()})
+
+if __name__ == "__main__":
+    err, every, twice = check()
+    print("max |X - rfft|:", err, " every slot written:", every, " written twice (bin 100 pairs with itself):", twice)
+    pats = {"+s": lambda s: s, "-s": lambda s: 100 - s, "+5s": lambda s: 5 * s, "-5s": lambda s: 100 - 5 * s}
+    for FS in range(200, 216):
+        print(FS, {k: wavefronts(FS, f) for k, f in pats.items()})
+

@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mfcc_lane5_kernel(const Params 
         const TIn* x_next = nullptr;
         if (g + g_step < n_groups) {
             x_next = frame_of(g + g_step, f_next, valid_next);
-            const char* pf = reinterpret_cast<const char*>(x_next + 40 * v10);
+            const char* pf = reinterpret_cast<const char*>(x_next + 40 * v10);   // this twin's 40 samples: first and last byte
             prefetch_l2(pf);
-            if (sizeof(TIn) == 4) prefetch_l2(pf + 128);
+            prefetch_l2(pf + 40 * sizeof(TIn) - 4);
         }
         // ---- pass A: global → window → radix 8 → twiddle → slots 25u + n1; butterflies i = 0..2 (h = 0) or 3, 4 (h = 1) ---------
         {
