@@ -356,7 +356,7 @@ def c1_record(args, reps=None):
     """BASELINE configs[0]: examples/pitch_detection.rs as shipped, timed on the CPU oracle (one thread, as shipped)."""
     import oracle
     oracle.build()
-    reps = reps or max(3, min(args.steps, 20))
+    reps = reps or max(3, min(args.steps if args.steps is not None else 20, 20))   # no --steps: 20 repetitions
     out = {"metric": C1["metric"], "unit": "frames/s", "higher_is_better": True, "dtype": "f64", "data": "synthetic sine + tests/fixtures/short_sample.wav",
            "config": {"workload": C1["workload"]}, "impl_note": "CPU oracle (C++ f64 port of the Rust reference), 1 thread, as shipped"}
     cases = {}

@@ -469,7 +469,7 @@ def test_roots_fixup_redoes_flagged_frames_in_f64(oracle, monkeypatch):
     c.profile_begin()
     mixed = c.lpc_to_resonances(ac, 12, True, float(fs))
     names = c.profile_end()
-    assert "lpc_roots_pair_kernel" in names and "lpc_roots_fixup_kernel" in names
+    assert "lpc_roots_pair_kernel" in names and "lpc_roots_rt_kernel<double> (fix-up launch)" in names
     a, b, m = pair["resonances"].to_host(), f64["resonances"].to_host(), mixed["resonances"].to_host()
     flagged = (np.arange(2 * J) % 7) == 0
     assert np.array_equal(m[flagged], b[flagged])

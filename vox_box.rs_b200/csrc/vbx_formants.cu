@@ -268,15 +268,15 @@ int launch_roots_fixup(vbx_ctx* ctx, const RootsParams& Q, int p, cudaStream_t s
     const size_t smem_fix = roots_rt_smem_bytes(p, false);
     VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_rt_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fix));
     const bool side = (stream != ctx->stream);
-    const int slot = side ? vbx_prof_range_begin(ctx, "lpc_roots_fixup_kernel", stream) : -1;
+    const int slot = side ? vbx_prof_range_begin(ctx, "lpc_roots_rt_kernel<double> (fix-up launch)", stream) : -1;
     lpc_roots_rt_kernel<double><<<vbx_ctx::kHardCap / kRootsThreads, kRootsThreads, smem_fix, stream>>>(Q2, p);
     if (side) {
         vbx_prof_range_end(ctx, slot, stream);
         const cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "launch of lpc_roots_fixup_kernel failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) return vbx_fail(ctx, VBX_ERR_CUDA, "launch of lpc_roots_rt_kernel<double> (fix-up) failed: %s", cudaGetErrorString(e));
         ctx->launches++;
     } else {
-        VBX_CHECK_LAUNCH(ctx, "lpc_roots_fixup_kernel");
+        VBX_CHECK_LAUNCH(ctx, "lpc_roots_rt_kernel<double> (fix-up launch)");
     }
     return VBX_OK;
 }
