@@ -109,6 +109,32 @@ def _ncu_traffic(profile_name):
         return None
 
 
+_NCU_KEYS = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_pct",
+             "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "pipe_fp64_pct",
+             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "pipe_fma_pct",
+             "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "pipe_lsu_pct",
+             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+             "launch__registers_per_thread": "registers",
+             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
+             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflict_wavefronts",
+             "gpu__time_duration.sum": "duration"}
+
+
+def _ncu_counters(profile_name):
+    """Key counters of a committed `ncu --set full` summary under profiles/ (tools/ncu_summary.sh): what the kernel's pipes
+    did in that capture — the cross-check of the fractions this run computes from its own timings (or None)."""
+    try:
+        out = {"profile": "profiles/" + profile_name}
+        for line in open(os.path.join(ROOT, "profiles", profile_name)):
+            m = re.match(r"([\w.]+) = ([0-9.]+) ?(\S*)", line)
+            if m and m.group(1) in _NCU_KEYS:
+                v = float(m.group(2))
+                out[_NCU_KEYS[m.group(1)]] = (v, m.group(3)) if m.group(1) == "gpu__time_duration.sum" else v
+        return out if len(out) > 1 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clock, power and throttle reasons of one GPU while the timed regions run (NVML; falls back to the
     nvidia-smi query line of /opt/skills/guides/B200_PROFILING.md).  Samples are time-stamped so that a leg can be
@@ -630,21 +656,21 @@ class Workload:
             "lpc": {"lpc_fused16_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), "r1_lpc16_final_full.txt", alg),
                     "lpc_fused_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), "r1_lpc_final_full.txt", alg),
                     "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), None, alg),
-                    "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), None, alg)},
+                    "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 2 * 4 * (p + 1), "r2_lpcp_v1_full.txt", alg)},
             "formants": {
                 "lpc_fused_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r1_lpc_final_full.txt", alg),
                 "lpc_fuseda_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r2_lpca_v1_full.txt", alg),
-                "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), None, alg),
+                "lpc_fusedp_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r2_lpcp_v1_full.txt", alg),
                 "lpc_fused16_kernel": ("fp64", lpc_flop, 4 * hop + 8 * (p + 1), "r1_lpc16_final_full.txt", alg),
-                "lpc_roots_pair_kernel": ("fp32", roots_flop, 8 * (p + 1) + 8 * p + 5, "r1_roots_final_full.txt", cnt),
+                "lpc_roots_pair_kernel": ("fp32", roots_flop, 8 * (p + 1) + 8 * p + 5, "r2_roots_v2_full.txt", cnt),
                 "lpc_roots_rt_kernel": ("fp32", roots_flop, 8 * (p + 1) + 8 * p + 5, None, cnt),
                 # latency-bound by construction (998 sequential steps per utterance): no pipe fraction is meaningful
                 "tracker_idx_kernel": (None, None, 8 * p + 4 + 4 * 8, "r1_tracker_final_full.txt", "latency-bound: sequential over the frames of an utterance"),
             },
             "pitch": {
-                "pitch_lag64_kernel": ("fp64", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, None, alg),
+                "pitch_lag64_kernel": ("fp64", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, "r2_lag64_v2_full.txt", alg),
                 "pitch_lag_kernel": ("fp32", 2.0 * N * (N + 1) / 2, 4 * hop + 8 * N, "r1_lag_final_full.txt", alg),
-                "pitch_refine8q_kernel": ("fp64", refine_flop, 8 * N, "r1_refine_final_full.txt", cnt_r),
+                "pitch_refine8q_kernel": ("fp64", refine_flop, 8 * N, "r2_refine2_v1_full.txt", cnt_r),
                 "pitch_finalize_kernel": (None, None, 16 * 16 + 140, None, "small"),
             },
             # mfcc_lane5_kernel: the fp64 instructions it EXECUTES (ncu source counters of profiles/r2_mfcc_lane5_v4_full.txt: 375
@@ -666,7 +692,9 @@ class Workload:
         for name, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             entry = {"ms_per_step": ms / steps, "launches_per_step": n / steps, "share": ms / total_ms}
             if name in table:
-                pipe, flop, byts, _, how = table[name]
+                pipe, flop, byts, prof_file, how = table[name]
+                if prof_file:
+                    entry["ncu"] = _ncu_counters(prof_file)
                 sec = ms * 1e-3 / steps
                 entry.update({"gbs": byts * self.F / sec / 1e9, "frac_hbm": byts * self.F / sec / 1e9 / hbm_peak, "work": how})
                 if pipe:
