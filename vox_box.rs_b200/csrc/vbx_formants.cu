@@ -293,8 +293,18 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
     // keeps the reference's one-root-at-a-time order for A/B runs
     const char* pe = getenv("VBX_ROOTS_PAIR");
     if (f32 && !Q.roots_out && !(pe && pe[0] == '0')) {
-        const size_t smem_pair = roots_pair_smem_bytes(p);
-        VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+        // 96-thread CTAs (24 KB at order 12) fit next to the persistent LPC kernel's CTA on an SM: ctx->roots_small
+        int rthreads = ctx->roots_small ? 96 : kRootsThreads;
+        if (const char* e = getenv("VBX_ROOTS_THREADS")) rthreads = atoi(e) == 96 ? 96 : kRootsThreads;
+        const size_t smem_pair = roots_pair_smem_bytes(p, rthreads);
+        if (rthreads == 96) {
+            VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+            // the same (maximum) shared-memory carve-out as the persistent LPC kernel's SMs: CTAs of kernels that want
+            // different carve-outs do not share an SM
+            VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel<96>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        }
+        else VBX_CUDA(ctx, cudaFuncSetAttribute(lpc_roots_pair_kernel<kRootsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+        const int64_t grid_pair = (Q.n_frames + rthreads - 1) / rthreads;
         RootsParams Q1 = Q;
         Q1.work = vbx_work_ptr(ctx);
         Q1.hard_list = ctx->hard_list;
@@ -302,7 +312,8 @@ int launch_lpc_roots(vbx_ctx* ctx, const RootsParams& Q, int p, int precision /*
         Q1.hard_cap = vbx_ctx::kHardCap;
         if (const char* e = getenv("VBX_ROOTS_FORCE_HARD")) Q1.hard_mod = atoi(e);
         VBX_CUDA(ctx, cudaMemsetAsync(Q1.hard_count, 0, sizeof(unsigned), ctx->stream));
-        lpc_roots_pair_kernel<<<(unsigned)grid, kRootsThreads, smem_pair, ctx->stream>>>(Q1, p);
+        if (rthreads == 96) lpc_roots_pair_kernel<96><<<(unsigned)grid_pair, 96, smem_pair, ctx->stream>>>(Q1, p);
+        else lpc_roots_pair_kernel<kRootsThreads><<<(unsigned)grid_pair, kRootsThreads, smem_pair, ctx->stream>>>(Q1, p);
         VBX_CHECK_LAUNCH(ctx, "lpc_roots_pair_kernel");
         // fix-up: frames on which a solve hit the 20-iteration cap twice (two start points) without converging go to the f64
         // reference-order kernel

@@ -59,6 +59,7 @@ struct vbx_ctx {
     // incremented only while profiling is on): see vbx_profile_counters in the header
     unsigned long long* work_counters = nullptr;
     int reserve_sms = 0;               // SMs the persistent kernels leave free for a co-running side-stream kernel
+    bool roots_small = false;          // lpc_roots_pair_kernel in 96-thread CTAs (they fit beside a persistent LPC CTA)
     unsigned* tile_counter = nullptr;  // device: [0] the persistent kernels' dynamic tile cursor, [1] length of hard_list
     int* hard_list = nullptr;          // device: frames the pair-deflation roots kernel hands to the f64 fix-up launch
     static constexpr int kHardCap = 4096;
