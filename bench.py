@@ -673,11 +673,11 @@ class Workload:
                 "pitch_refine8q_kernel": ("fp64", refine_flop, 8 * N, "r2_refine2_v1_full.txt", cnt_r),
                 "pitch_finalize_kernel": (None, None, 16 * 16 + 140, None, "small"),
             },
-            # mfcc_lane5_kernel: the fp64 instructions it EXECUTES (ncu source counters of profiles/r2_mfcc_lane5_v4_full.txt: 375
+            # mfcc_lane5_kernel: the fp64 instructions it EXECUTES (ncu source counters of profiles/r2_mfcc_lane5_v5_full.txt: 390
             # warp-wide DFMA / DADD / DMUL per frame, the same for every frame), each charged as one FMA issue slot of 32 lanes —
             # i.e. the fraction is the fp64 pipe's utilisation; the kernel's other limit is the shared-memory data path (DESIGN K8)
-            "mfcc": {"mfcc_lane5_kernel": ("fp64", 375.0 * 64, 4 * hop + 4 * 13, "r2_mfcc_lane5_v4_full.txt",
-                                           "executed: 375 fp64 warp instructions per frame (ncu), each an FMA issue slot"),
+            "mfcc": {"mfcc_lane5_kernel": ("fp64", 390.0 * 64, 4 * hop + 4 * 13, "r2_mfcc_lane5_v5_full.txt",
+                                           "executed: 390 fp64 warp instructions per frame (ncu), each an FMA issue slot"),
                      "mfcc_warp_kernel": ("fp64", 19.5e3, 4 * hop + 4 * 13, "r1_mfcc_final_full.txt", alg),
                      "mfcc_kernel": ("fp64", 19.5e3, 4 * hop + 4 * 13, None, alg)},
         }[cfg["kind"]]

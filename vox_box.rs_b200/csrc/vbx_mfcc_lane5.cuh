@@ -486,7 +486,7 @@ static bool build_tables(Tables& T, const int* bins, int num_coeffs, const doubl
             T.u4slot[(2 * op + 1) * 5 + s] = (unsigned short)l5_slot(kb[op]);
         }
     }
-    // the intervals sorted by length, five at a time to warp 0, warp 1, warp 0, ... (see Tables).  Within a round the five lanes
+    // the intervals sorted by length, five at a time to warp 0, 1, 1, 0, 0, 1, 1, ... (see Tables).  Within a round the five lanes
     // walk five different intervals in lock step and read one spectrum slot each per step: which lane takes which interval, and
     // how many zero-slot entries are put IN FRONT of each (0..3, shifting its phase), is chosen by simulating the shared-memory
     // wavefronts of the round's steps (16-byte accesses are served per quarter warp; two lanes collide when their slots share a
@@ -519,7 +519,7 @@ static bool build_tables(Tables& T, const int* bins, int num_coeffs, const doubl
     int n[2 * LPF] = {0}, nw[2 * LPF] = {0};
     T.n_rounds[0] = T.n_rounds[1] = 0;
     for (size_t first = 0, turn = 0; first < iv.size(); first += LPF, ++turn) {
-        const int hh = (int)(turn & 1);
+        const int hh = (int)(((turn + 1) >> 1) & 1);   // warp 0, 1, 1, 0, 0, 1, 1, ...: the sorted lengths' sums stay level
         const int r = T.n_rounds[hh]++;
         int4 mem[LPF];
         for (int i = 0; i < LPF; ++i) mem[i] = (first + i < iv.size()) ? iv[first + i] : make_int4((int)kIdle, 0, 0, 0);
