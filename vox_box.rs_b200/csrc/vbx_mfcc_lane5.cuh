@@ -8,8 +8,9 @@
 //
 //   The real frame is packed as z[n] = x[2n]·w[2n] + i·x[2n+1]·w[2n+1], n < 200, and transformed IN PLACE by
 //   decimation-in-frequency passes of radix 8, 5, 5 (k = kA + 8·kB + 40·kC):
-//     pass A  butterfly n1 = s + 5i (i < 5): inputs z[n1 + 25t] straight from global memory (windowed in fp64), radix 8, output
-//             u times W200^(n1·u) to slot 25u + n1;
+//     pass A  butterfly n1 (< 25): inputs z[n1 + 25t] straight from global memory (windowed in fp64), radix 8, output u times
+//             W200^(n1·u) to slot 25u + n1.  (In this pass alone a lane owns a POSITION n1 = lane and walks three of the group's
+//             frames with its seven twiddles in registers; everywhere else lane = 5·q + s works on frame q.)
 //     pass B  inside every 25-block b (= kA) butterfly j = s: inputs 25b + s + 5t, radix 5, output kB times W25^(s·kB) (the four
 //             twiddles live in registers), stored TRANSPOSED to 25b + 5s + col(b, kB) (four blocks in flight, __syncwarp between
 //             their loads and stores);
